@@ -1,0 +1,5 @@
+"""Alias of caduceus_b200.configuration_caduceus (same module path as ref:caduceus/configuration_caduceus.py)."""
+from caduceus_b200.configuration_caduceus import *  # noqa: F401,F403
+from caduceus_b200 import configuration_caduceus as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

@@ -1,0 +1,109 @@
+"""ctypes binding of the C-ABI in include/caduceus_b200.h.
+
+The product path has NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised
+(UPSTREAM raised through TORCH_CHECK -> RuntimeError; SURVEY.md §8b "Errors").
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcaduceus_b200.so")
+
+CAD_F32, CAD_F16, CAD_BF16 = 0, 1, 2
+ABI_VERSION = 1
+
+_p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+
+class EmbeddingArgs(C.Structure):
+    _fields_ = [("ids", _p), ("weight", _p), ("cmap", _p), ("out", _p),
+                ("B", _i64), ("L", _i64), ("V", _i64), ("D", _i64), ("rcps", _i32), ("dtype", _i32)]
+
+
+class EmbeddingBwdArgs(C.Structure):
+    _fields_ = [("ids", _p), ("cmap", _p), ("dout", _p), ("dweight", _p),
+                ("B", _i64), ("L", _i64), ("V", _i64), ("D", _i64), ("rcps", _i32), ("dtype", _i32)]
+
+
+class AddNormArgs(C.Structure):
+    _fields_ = [("x", _p), ("residual", _p), ("weight", _p), ("bias", _p), ("y", _p), ("res_out", _p),
+                ("rstd", _p), ("mean", _p),
+                ("rows", _i64), ("D", _i64), ("ldx", _i64), ("ldr", _i64), ("ldy", _i64), ("ldo", _i64),
+                ("nhalf", _i32), ("swap", _i32), ("wflip_mask", _i32), ("is_rms", _i32),
+                ("xdtype", _i32), ("wdtype", _i32), ("res_in_dtype", _i32), ("res_out_dtype", _i32),
+                ("eps", _f32)]
+
+
+class AddNormBwdArgs(C.Structure):
+    _fields_ = [("dy", _p), ("dres_out", _p), ("v", _p), ("weight", _p), ("rstd", _p), ("mean", _p),
+                ("dx", _p), ("dweight_partial", _p), ("dbias_partial", _p),
+                ("rows", _i64), ("D", _i64), ("lddy", _i64), ("lddr", _i64), ("ldv", _i64), ("lddx", _i64),
+                ("nhalf", _i32), ("swap", _i32), ("wflip_mask", _i32), ("is_rms", _i32), ("has_bias", _i32),
+                ("dydtype", _i32), ("vdtype", _i32), ("wdtype", _i32), ("dxdtype", _i32), ("drdtype", _i32),
+                ("nblocks", _i32)]
+
+
+class ScanFwdArgs(C.Structure):
+    _fields_ = [("xz", _p), ("xdbl", _p), ("out", _p),
+                ("conv_w", _p), ("conv_b", _p), ("dt_w", _p), ("dt_b", _p), ("A2", _p), ("Dskip", _p),
+                ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p),
+                ("halo", _p), ("h0", _p), ("hlast", _p), ("dtsum", _p), ("chunk_state", _p),
+                ("L", _i64), ("E", _i64), ("N", _i64), ("R", _i64), ("K", _i64),
+                ("ldxz", _i64), ("ldxd", _i64), ("ldo", _i64),
+                ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32)]
+
+
+class ConvFwdArgs(C.Structure):
+    _fields_ = [("xz", _p), ("u", _p), ("conv_w", _p), ("conv_b", _p),
+                ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
+                ("L", _i64), ("E", _i64), ("ldxz", _i64), ("ldu", _i64),
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32)]
+
+
+# every symbol include/caduceus_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "cad_version": (C.c_int, []),
+    "cad_last_error": (C.c_char_p, []),
+    "cad_sm_count": (C.c_int, []),
+    "cad_embedding_fwd": (C.c_int, [C.POINTER(EmbeddingArgs), _p]),
+    "cad_embedding_bwd": (C.c_int, [C.POINTER(EmbeddingBwdArgs), _p]),
+    "cad_add_norm_fwd": (C.c_int, [C.POINTER(AddNormArgs), _p]),
+    "cad_add_norm_bwd": (C.c_int, [C.POINTER(AddNormBwdArgs), _p]),
+    "cad_add_norm_bwd_blocks": (C.c_int, [_i64]),
+    "cad_bimamba_scan_fwd": (C.c_int, [C.POINTER(ScanFwdArgs), _p]),
+    "cad_scan_chunk_len": (C.c_int, []),
+    "cad_conv_silu_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), _p]),
+    "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"caduceus_b200: CUDA library not built ({LIB_PATH} missing). Run `python -m caduceus_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU / eager fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)     # AttributeError if the .so does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        if lib.cad_version() != ABI_VERSION:
+            raise RuntimeError(f"caduceus_b200: ABI mismatch (library {lib.cad_version()}, binding {ABI_VERSION}); rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cad_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

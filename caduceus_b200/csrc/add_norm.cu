@@ -1,0 +1,333 @@
+// Fused residual-add + RMSNorm / LayerNorm, forward and backward, with the RC-equivariant (two-half)
+// variants folded into the addressing.
+//
+// Replaces upstream's Triton `_layer_norm_fwd_1pass_kernel` / `_layer_norm_bwd_kernel` reached through
+// rms_norm_fn / layer_norm_fn at ref:caduceus/modeling_caduceus.py:244-273 and
+// ref:caduceus/modeling_rcps.py:177-195, and the flips/cats the reference wraps around them:
+//   flip_{L,C}(N_w(flip_{L,C}(v)))[l, c] = v[l, c] * rstd(v[l, :]) * w[D-1-c]
+// i.e. the RC half is a plain row norm with the weight vector read backwards — no data movement.
+//
+// HBM-bound: one warp per (token, half) row, 128-bit accesses, one pass (row held in registers).
+#include "common.cuh"
+
+namespace cad {
+
+// 8 consecutive elements starting at element offset `off` of a buffer of runtime dtype.
+__device__ __forceinline__ void load8(const void* base, int dtype, int64_t off, float (&v)[8]) {
+  if (dtype == CAD_F32) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + off);
+    float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + off));
+    if (dtype == CAD_BF16) {
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __bfloat162float(e[k]);
+    } else {
+      const __half* e = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __half2float(e[k]);
+    }
+  }
+}
+__device__ __forceinline__ void store8(void* base, int dtype, int64_t off, const float (&v)[8]) {
+  if (dtype == CAD_F32) {
+    float4* p = reinterpret_cast<float4*>(static_cast<float*>(base) + off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 raw;
+    if (dtype == CAD_BF16) {
+      __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = __float2bfloat16_rn(v[k]);
+    } else {
+      __half* e = reinterpret_cast<__half*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = __float2half_rn(v[k]);
+    }
+    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + off) = raw;
+  }
+}
+// round v through dtype (what the stored value will read back as)
+__device__ __forceinline__ float round_to(float v, int dtype) {
+  if (dtype == CAD_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  if (dtype == CAD_F16) return __half2float(__float2half_rn(v));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ITER = 8-element chunks per lane; D <= 256 * ITER.
+template <int ITER>
+__global__ void __launch_bounds__(256) add_norm_fwd_kernel(cad_add_norm_args a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t nrow = a.rows * a.nhalf;
+  const int64_t D = a.D;
+  const float invD = 1.0f / (float)D;
+
+  for (int64_t rh = warp; rh < nrow; rh += nwarps) {
+    const int64_t r = rh / a.nhalf;
+    const int h = (int)(rh - r * a.nhalf);
+    const int hin = h ^ a.swap;
+    const bool wflip = (a.wflip_mask >> h) & 1;
+
+    float v[ITER][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+      const int64_t c = (int64_t)(i * 32 + lane) * 8;
+      if (c < D) {
+        load8(a.x, a.xdtype, r * a.ldx + hin * D + c, v[i]);
+        if (a.residual) {
+          float rr[8];
+          load8(a.residual, a.res_in_dtype, r * a.ldr + hin * D + c, rr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[i][k] += rr[k];
+        }
+        if (a.res_out) store8(a.res_out, a.res_out_dtype, r * a.ldo + h * D + c, v[i]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s1 += v[i][k]; s2 += v[i][k] * v[i][k]; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
+      }
+    }
+    float mean = 0.f, rstd;
+    if (a.is_rms) {
+      s2 = warp_sum(s2);
+      rstd = rsqrtf(s2 * invD + a.eps);
+    } else {
+      s1 = warp_sum(s1);
+      mean = s1 * invD;
+      float q = 0.f;                       // two-pass variance on the register copy (no cancellation)
+#pragma unroll
+      for (int i = 0; i < ITER; ++i) {
+        const int64_t c = (int64_t)(i * 32 + lane) * 8;
+        if (c < D) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { float d = v[i][k] - mean; q += d * d; }
+        }
+      }
+      q = warp_sum(q);
+      rstd = rsqrtf(q * invD + a.eps);
+    }
+    if (lane == 0) {
+      if (a.rstd) a.rstd[rh] = rstd;
+      if (a.mean) a.mean[rh] = mean;
+    }
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+      const int64_t c = (int64_t)(i * 32 + lane) * 8;
+      if (c < D) {
+        float w[8], y[8];
+        if (!wflip) {
+          load8(a.weight, a.wdtype, c, w);
+        } else {
+          float t[8];
+          load8(a.weight, a.wdtype, D - 8 - c, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = t[7 - k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = (v[i][k] - mean) * rstd * w[k];
+        if (a.bias) {
+          float b[8];
+          if (!wflip) {
+            load8(a.bias, a.wdtype, c, b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] += b[k];
+          } else {
+            load8(a.bias, a.wdtype, D - 8 - c, b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] += b[7 - k];
+          }
+        }
+        store8(a.y, a.xdtype, r * a.ldy + h * D + c, y);
+      }
+    }
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------
+// With g = dy * w', xhat = (v - mean) * rstd:
+//   RMS:  dv = rstd * (g - xhat * mean_c(g * xhat))            LN: dv = rstd * (g - mean_c(g) - xhat * mean_c(g*xhat))
+//   dv += dres_out;   dw'[c] += dy * xhat;   db'[c] += dy
+// dv of output half h is the gradient of INPUT half hin = h ^ swap (x and residual share it).
+// Weight/bias gradients are accumulated per block into (nblocks, D) partials (row-serial inside a warp, then
+// a shared-memory reduction over the block's warps) and summed by the caller: deterministic, no atomics.
+template <int ITER>
+__global__ void __launch_bounds__(256) add_norm_bwd_kernel(cad_add_norm_bwd_args a) {
+  extern __shared__ float red[];    // (warps, D) for dweight, then (warps, D) for dbias
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * wpb + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * wpb;
+  const int64_t nrow = a.rows * a.nhalf;
+  const int64_t D = a.D;
+  const float invD = 1.0f / (float)D;
+
+  float dw[ITER][8], db[ITER][8];
+#pragma unroll
+  for (int i = 0; i < ITER; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dw[i][k] = 0.f; db[i][k] = 0.f; }
+
+  for (int64_t rh = warp; rh < nrow; rh += nwarps) {
+    const int64_t r = rh / a.nhalf;
+    const int h = (int)(rh - r * a.nhalf);
+    const int hin = h ^ a.swap;
+    const bool wflip = (a.wflip_mask >> h) & 1;
+    const float rstd = a.rstd[rh];
+    const float mean = a.is_rms ? 0.f : a.mean[rh];
+
+    float g[ITER][8], xh[ITER][8];
+    float s_g = 0.f, s_gx = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+      const int64_t c = (int64_t)(i * 32 + lane) * 8;
+      if (c < D) {
+        float dy[8], v[8], w[8];
+        load8(a.dy, a.dydtype, r * a.lddy + h * D + c, dy);
+        load8(a.v, a.vdtype, r * a.ldv + h * D + c, v);
+        if (!wflip) {
+          load8(a.weight, a.wdtype, c, w);
+        } else {
+          float t[8];
+          load8(a.weight, a.wdtype, D - 8 - c, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = t[7 - k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xh[i][k] = (v[k] - mean) * rstd;
+          g[i][k] = dy[k] * w[k];
+          s_g += g[i][k];
+          s_gx += g[i][k] * xh[i][k];
+          // weight-gradient slots are indexed by the UNFLIPPED weight position
+          const int kk = wflip ? 7 - k : k;
+          dw[i][kk] += dy[k] * xh[i][k];
+          db[i][kk] += dy[k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { g[i][k] = 0.f; xh[i][k] = 0.f; }
+      }
+    }
+    s_gx = warp_sum(s_gx) * invD;
+    s_g = a.is_rms ? 0.f : warp_sum(s_g) * invD;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+      const int64_t c = (int64_t)(i * 32 + lane) * 8;
+      if (c < D) {
+        float dv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dv[k] = rstd * (g[i][k] - s_g - xh[i][k] * s_gx);
+        if (a.dres_out) {
+          float dr[8];
+          load8(a.dres_out, a.drdtype, r * a.lddr + h * D + c, dr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dv[k] += dr[k];
+        }
+        store8(a.dx, a.dxdtype, r * a.lddx + hin * D + c, dv);
+      }
+    }
+  }
+
+  // block reduction of the weight/bias partials.  A lane's chunk i covers unflipped columns
+  // c..c+7 for non-flipped halves and D-8-c..D-1-c for flipped halves; both were folded into `kk` above only
+  // within the 8-chunk, so flipped rows must also mirror the chunk position: handle by writing flipped
+  // contributions to mirrored columns.  To keep one accumulator set, rows of flipped halves are processed by
+  // the same warp as non-flipped rows only when nhalf == 1; with nhalf == 2 warps alternate halves, so we keep
+  // the accumulators per (half parity) implicitly: rh parity == h when nwarps is even.
+  float* rw = red;
+  float* rb = red + (int64_t)wpb * D;
+  // Determine whether this warp's rows were flipped halves (nwarps is forced even by the launcher, so a warp
+  // sees a single half h = warp % nhalf for nhalf == 2).
+  const int hw = (a.nhalf == 2) ? (int)(warp & 1) : 0;
+  const bool wflip_w = (a.wflip_mask >> hw) & 1;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int64_t c = (int64_t)(i * 32 + lane) * 8;
+    if (c < D) {
+      const int64_t cc = wflip_w ? D - 8 - c : c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { rw[(int64_t)wib * D + cc + k] = dw[i][k]; rb[(int64_t)wib * D + cc + k] = db[i][k]; }
+    }
+  }
+  __syncthreads();
+  for (int64_t c = threadIdx.x; c < D; c += blockDim.x) {
+    float sw = 0.f, sb = 0.f;
+    for (int w = 0; w < wpb; ++w) { sw += rw[(int64_t)w * D + c]; sb += rb[(int64_t)w * D + c]; }
+    a.dweight_partial[(int64_t)blockIdx.x * D + c] = sw;
+    if (a.has_bias) a.dbias_partial[(int64_t)blockIdx.x * D + c] = sb;
+  }
+}
+
+static int norm_grid(int64_t nrow, int threads) {
+  const int wpb = threads / 32;
+  int64_t blocks = (nrow + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)cad_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace cad
+
+extern "C" int cad_add_norm_fwd(const cad_add_norm_args* a, void* stream_) {
+  using namespace cad;
+  CAD_REQUIRE(a && a->x && a->weight && a->y, "cad_add_norm_fwd: null pointer");
+  CAD_REQUIRE(a->nhalf == 1 || a->nhalf == 2, "cad_add_norm_fwd: nhalf must be 1 or 2");
+  CAD_REQUIRE(a->D > 0 && a->D % 8 == 0 && a->D <= 2048, "cad_add_norm_fwd: D (%lld) must be a multiple of 8, <= 2048",
+              (long long)a->D);
+  CAD_REQUIRE(a->ldx % 8 == 0 && a->ldy % 8 == 0 && (!a->residual || a->ldr % 8 == 0) &&
+              (!a->res_out || a->ldo % 8 == 0), "cad_add_norm_fwd: row pitches must be multiples of 8 elements");
+  CAD_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->weight) && aligned16(a->residual) &&
+              aligned16(a->res_out) && aligned16(a->bias), "cad_add_norm_fwd: pointers must be 16B aligned");
+  CAD_REQUIRE(a->swap == 0 || a->nhalf == 2, "cad_add_norm_fwd: swap needs nhalf == 2");
+  if (a->rows == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int threads = 256;
+  const int blocks = norm_grid(a->rows * a->nhalf, threads);
+  if (a->D <= 256) add_norm_fwd_kernel<1><<<blocks, threads, 0, stream>>>(*a);
+  else if (a->D <= 512) add_norm_fwd_kernel<2><<<blocks, threads, 0, stream>>>(*a);
+  else if (a->D <= 1024) add_norm_fwd_kernel<4><<<blocks, threads, 0, stream>>>(*a);
+  else add_norm_fwd_kernel<8><<<blocks, threads, 0, stream>>>(*a);
+  CAD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cad_add_norm_bwd_blocks(int64_t rows) {
+  int b = cad::norm_grid(rows, 256);
+  int cap = cad_sm_count() * 2;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : b;
+}
+
+extern "C" int cad_add_norm_bwd(const cad_add_norm_bwd_args* a, void* stream_) {
+  using namespace cad;
+  CAD_REQUIRE(a && a->dy && a->v && a->weight && a->rstd && a->dx && a->dweight_partial,
+              "cad_add_norm_bwd: null pointer");
+  CAD_REQUIRE(a->is_rms || a->mean, "cad_add_norm_bwd: LayerNorm needs the saved mean");
+  CAD_REQUIRE(!a->has_bias || a->dbias_partial, "cad_add_norm_bwd: bias gradient buffer missing");
+  CAD_REQUIRE(a->nhalf == 1 || a->nhalf == 2, "cad_add_norm_bwd: nhalf must be 1 or 2");
+  CAD_REQUIRE(a->D > 0 && a->D % 8 == 0 && a->D <= 1024, "cad_add_norm_bwd: D must be a multiple of 8, <= 1024");
+  CAD_REQUIRE(a->lddy % 8 == 0 && a->ldv % 8 == 0 && a->lddx % 8 == 0 && (!a->dres_out || a->lddr % 8 == 0),
+              "cad_add_norm_bwd: row pitches must be multiples of 8 elements");
+  CAD_REQUIRE(a->nblocks >= 1, "cad_add_norm_bwd: nblocks");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int threads = 256;   // 8 warps: even, so with nhalf == 2 every warp sees one half only
+  const size_t smem = (size_t)2 * (threads / 32) * a->D * sizeof(float);
+  if (a->D <= 256) add_norm_bwd_kernel<1><<<a->nblocks, threads, smem, stream>>>(*a);
+  else if (a->D <= 512) add_norm_bwd_kernel<2><<<a->nblocks, threads, smem, stream>>>(*a);
+  else add_norm_bwd_kernel<4><<<a->nblocks, threads, smem, stream>>>(*a);
+  CAD_LAUNCH_CHECK();
+  return 0;
+}

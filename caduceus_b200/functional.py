@@ -1,0 +1,260 @@
+"""Host-side wrappers over the C-ABI kernels: tensors in, tensors out, autograd where the path trains.
+
+PyTorch is plumbing here (device memory, streams, the dense cuBLAS projections); the arithmetic of the hot
+path is in csrc/*.cu.  Every function raises RuntimeError on non-CUDA tensors — there is no CPU fallback.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import CAD_BF16, CAD_F16, CAD_F32
+
+_DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"caduceus_b200: unsupported dtype {t.dtype} (float32 / float16 / bfloat16 only)")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "caduceus_b200: the hot path runs only on CUDA tensors (sm_100a kernels); there is no CPU fallback. "
+                "Use the oracle under oracle/ for CPU reference numbers.")
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _rows(t, width):
+    """View t (..., width) as (rows, width) with a uniform row pitch; copies only when it cannot be a view."""
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    try:
+        v = t.view(-1, width)
+    except RuntimeError:
+        v = t.contiguous().view(-1, width)
+    pitch = v.stride(0) if v.shape[0] > 1 else width
+    if pitch < width or pitch % 8 != 0 or v.data_ptr() % 16 != 0:
+        v = v.contiguous()
+        pitch = width
+    return v, v.shape[0], pitch
+
+
+# =====================================================================================================
+# embedding
+# =====================================================================================================
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, weight, cmap):
+        _require_cuda(ids, weight, cmap)
+        lib = _lib.load()
+        ids = ids.contiguous().long()
+        w = weight.contiguous()
+        B, L = ids.shape
+        V, D = w.shape
+        rcps = cmap is not None
+        out = torch.empty(B, L, 2 * D if rcps else D, device=w.device, dtype=w.dtype)
+        a = _lib.EmbeddingArgs(_ptr(ids), _ptr(w), _ptr(cmap), _ptr(out), B, L, V, D, int(rcps), _dt(w))
+        _lib.check(lib.cad_embedding_fwd(C.byref(a), _stream()), "cad_embedding_fwd")
+        ctx.save_for_backward(ids, cmap)
+        ctx.shape = (V, D, w.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, cmap = ctx.saved_tensors
+        V, D, wdtype = ctx.shape
+        lib = _lib.load()
+        dout = dout.contiguous()
+        B, L = ids.shape
+        dw = torch.zeros(V, D, device=dout.device, dtype=torch.float32)
+        a = _lib.EmbeddingBwdArgs(_ptr(ids), _ptr(cmap), _ptr(dout), _ptr(dw), B, L, V, D, int(cmap is not None),
+                                  _dt(dout))
+        _lib.check(lib.cad_embedding_bwd(C.byref(a), _stream()), "cad_embedding_bwd")
+        return None, dw.to(wdtype), None
+
+
+def embedding(ids, weight, cmap=None):
+    """Ph: W[ids].  PS (cmap given): cat[W[ids], W[cmap[ids]][..., ::-1]]  ==  ref:caduceus/modeling_rcps.py:54-67."""
+    return _EmbeddingFn.apply(ids, weight, cmap)
+
+
+# =====================================================================================================
+# fused add + RMSNorm / LayerNorm
+# =====================================================================================================
+class _AddNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps, is_rms, want_res, residual_in_fp32, nhalf, swap, wflip_mask):
+        _require_cuda(x, residual, weight, bias)
+        lib = _lib.load()
+        width = x.shape[-1]
+        D = width // nhalf
+        shape = x.shape
+        x2, rows, ldx = _rows(x, width)
+        r2, ldr = None, 0
+        if residual is not None:
+            assert residual.shape == x.shape
+            r2, _, ldr = _rows(residual, width)
+        w = weight.contiguous()
+        b = bias.contiguous() if bias is not None else None
+        if b is not None and b.dtype != w.dtype:
+            b = b.to(w.dtype)
+        needs_grad = any(ctx.needs_input_grad[:4])
+        res_dtype = torch.float32 if residual_in_fp32 else x.dtype
+        y = torch.empty(shape, device=x.device, dtype=x.dtype)
+        # the pre-norm sum is written when the caller wants it, or (training) to feed the backward
+        store_res = want_res or needs_grad
+        res_out = torch.empty(shape, device=x.device, dtype=res_dtype) if store_res else None
+        rstd = torch.empty(rows * nhalf, device=x.device, dtype=torch.float32) if needs_grad else None
+        mean = torch.empty(rows * nhalf, device=x.device, dtype=torch.float32) if (needs_grad and not is_rms) else None
+        a = _lib.AddNormArgs(
+            _ptr(x2), _ptr(r2), _ptr(w), _ptr(b), _ptr(y), _ptr(res_out), _ptr(rstd), _ptr(mean),
+            rows, D, ldx, ldr, width, width, nhalf, swap, wflip_mask, int(is_rms),
+            _dt(x2), _dt(w), _dt(r2) if r2 is not None else CAD_F32, _DT[res_dtype], float(eps))
+        _lib.check(lib.cad_add_norm_fwd(C.byref(a), _stream()), "cad_add_norm_fwd")
+        if needs_grad:
+            ctx.save_for_backward(res_out, w, rstd, mean)
+            ctx.meta = (rows, D, width, nhalf, swap, wflip_mask, is_rms, b is not None, x.dtype,
+                        None if residual is None else residual.dtype, weight.dtype,
+                        None if bias is None else bias.dtype, shape)
+        if want_res:
+            return y, res_out
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        res_out, w, rstd, mean = ctx.saved_tensors
+        rows, D, width, nhalf, swap, wflip_mask, is_rms, has_bias, xdtype, rdtype, wdtype, bdtype, shape = ctx.meta
+        lib = _lib.load()
+        if dy is None:
+            dy = torch.zeros(shape, device=res_out.device, dtype=xdtype)
+        dy2, _, lddy = _rows(dy, width)
+        dr2, lddr = None, 0
+        if dres is not None:
+            dr2, _, lddr = _rows(dres, width)
+        # gradient of the (x + residual) sum; kept in fp32 when the residual stream is fp32
+        gdtype = torch.float32 if (rdtype == torch.float32 or res_out.dtype == torch.float32) else xdtype
+        dx = torch.empty(shape, device=dy.device, dtype=gdtype)
+        nblocks = lib.cad_add_norm_bwd_blocks(rows * nhalf)
+        dwp = torch.empty(nblocks, D, device=dy.device, dtype=torch.float32)
+        dbp = torch.empty(nblocks, D, device=dy.device, dtype=torch.float32) if has_bias else None
+        a = _lib.AddNormBwdArgs(
+            _ptr(dy2), _ptr(dr2), _ptr(res_out), _ptr(w), _ptr(rstd), _ptr(mean), _ptr(dx), _ptr(dwp), _ptr(dbp),
+            rows, D, lddy, lddr, width, width, nhalf, swap, wflip_mask, int(is_rms), int(has_bias),
+            _dt(dy2), _dt(res_out), _dt(w), _DT[gdtype], _dt(dr2) if dr2 is not None else CAD_F32, nblocks)
+        _lib.check(lib.cad_add_norm_bwd(C.byref(a), _stream()), "cad_add_norm_bwd")
+        dw = dwp.sum(0).to(wdtype)
+        db = dbp.sum(0).to(bdtype) if has_bias else None
+        gx = dx if dx.dtype == xdtype else dx.to(xdtype)
+        gr = None
+        if rdtype is not None:
+            gr = dx if dx.dtype == rdtype else dx.to(rdtype)
+        return gx, gr, dw, db, None, None, None, None, None, None, None
+
+
+def add_norm(x, weight, bias=None, residual=None, eps=1e-5, is_rms=True, prenorm=False, residual_in_fp32=False,
+             nhalf=1, swap=0, wflip_mask=0):
+    """y = norm(x + residual) * w (+ b) per D-wide half; returns y or (y, x + residual).
+
+    nhalf=2 covers the RC-equivariant blocks with no flips or cats (see include/caduceus_b200.h):
+      fused RCPSMambaBlock (ref:caduceus/modeling_rcps.py:174-197): swap=1, wflip_mask=2
+      RCPSAddNormWrapper / final norm (ref:caduceus/modeling_rcps.py:107-130,
+      ref:caduceus/modeling_caduceus.py:242-262): swap=0, wflip_mask=2
+    """
+    y, res = _AddNormFn.apply(x, residual, weight, bias, eps, is_rms, prenorm, residual_in_fp32, nhalf, swap,
+                              wflip_mask)
+    return (y, res) if prenorm else y
+
+
+# =====================================================================================================
+# BiMamba inner path
+# =====================================================================================================
+_JOB_CACHE = {}
+
+
+def job_tables(nbatch, nstrand, ndir, untied_in, device):
+    """Device int32 tables (seq_of_job, pset_of_job, rev_of_job) for jobs ordered (batch, strand, direction).
+
+    Strand 1 is the reverse-complement strand of RCPSWrapper (ref:caduceus/modeling_rcps.py:95-99): its input is
+    time-reversed, so mamba_fwd's parameters run right-to-left there and mamba_rev's left-to-right
+    (SURVEY.md A.6): rev = direction XOR strand.
+    """
+    key = (nbatch, nstrand, ndir, untied_in, str(device))
+    hit = _JOB_CACHE.get(key)
+    if hit is not None:
+        return hit
+    seq, pset, rev = [], [], []
+    nw = ndir if untied_in else 1
+    for b in range(nbatch):
+        for s in range(nstrand):
+            for d in range(ndir):
+                seq.append((b * nstrand + s) * nw + (d if untied_in else 0))
+                pset.append(d)
+                rev.append(d ^ s)
+    t = tuple(torch.tensor(v, dtype=torch.int32, device=device) for v in (seq, pset, rev))
+    _JOB_CACHE[key] = t
+    return t
+
+
+def conv_silu(xz, conv_w4, conv_b, jobs, L, halo=None):
+    """v1 helper: u[job] = silu((anti)causal conv of x rows) -> (njobs, E, ldxz)."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    nseq, twoE, ld = xz.shape
+    E = twoE // 2
+    njobs = seq.numel()
+    u = torch.empty(njobs, E, ld, device=xz.device, dtype=xz.dtype)
+    a = _lib.ConvFwdArgs(_ptr(xz), _ptr(u), _ptr(conv_w4), _ptr(conv_b), _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo),
+                         L, E, ld, ld, nseq, njobs, _dt(xz))
+    _lib.check(lib.cad_conv_silu_fwd(C.byref(a), _stream()), "cad_conv_silu_fwd")
+    return u
+
+
+def scan_fwd(xz, xdbl, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
+             channels_per_cta=0):
+    """Launch the fused bidirectional scan.  xz (nseq, 2E, ld), xdbl (njobs, R+2N, ld) -> out (njobs, E, ld)."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    conv_w4, conv_b, dt_w, dt_b, A2, Dk = packed
+    nseq, twoE, ldxz = xz.shape
+    E = twoE // 2
+    njobs, rows, ldxd = xdbl.shape
+    P, _, N = A2.shape
+    R = dt_w.shape[-1]
+    assert rows == R + 2 * N
+    out = torch.empty(njobs, E, ldxz, device=xz.device, dtype=xz.dtype)
+    hlast = torch.empty(njobs, E, N, device=xz.device, dtype=torch.float32) if want_state else None
+    dtsum = torch.empty(njobs, E, device=xz.device, dtype=torch.float32) if want_state else None
+    chunk = lib.cad_scan_chunk_len()
+    nchunks = (L + chunk - 1) // chunk
+    cstate = (torch.empty(njobs, E, nchunks, N, device=xz.device, dtype=torch.float32)
+              if want_chunk_state else None)
+    a = _lib.ScanFwdArgs(
+        _ptr(xz), _ptr(xdbl), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_w), _ptr(dt_b), _ptr(A2), _ptr(Dk),
+        _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
+        L, E, N, R, 4, ldxz, ldxd, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta)
+    _lib.check(lib.cad_bimamba_scan_fwd(C.byref(a), _stream()), "cad_bimamba_scan_fwd")
+    return out, hlast, dtsum, cstate
+
+
+def microbench(which):
+    lib = _lib.load()
+    v = C.c_double(0.0)
+    _lib.check(lib.cad_microbench(int(which), C.byref(v), _stream()), "cad_microbench")
+    return v.value

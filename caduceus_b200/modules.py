@@ -1,0 +1,294 @@
+"""Operator-level API of the hot path: drop-in mirrors of the five upstream `mamba_ssm` symbols the reference
+imports (ref:caduceus/modeling_caduceus.py:11-27, ref:caduceus/modeling_rcps.py:12-18) —
+
+    Mamba, Block                                  (mamba_ssm.modules.mamba_simple)
+    RMSNorm, rms_norm_fn, layer_norm_fn           (mamba_ssm.ops.triton.layernorm)
+
+with the same constructor signatures, parameter names/shapes (so `state_dict` keys match) and call
+conventions — backed by the sm_100a kernels of this package instead of upstream's CUDA/Triton.  On top of
+them `bimamba_inner` runs BOTH directions (and both RC strands) of a BiMamba call through one fused launch.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import functional as CF
+
+_LOG2E = 1.4426950408889634
+
+
+# =====================================================================================================
+# norms
+# =====================================================================================================
+def rms_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False):
+    """Same contract as upstream's Triton `rms_norm_fn`; accepts strided row views."""
+    return CF.add_norm(x, weight, bias, residual=residual, eps=eps, is_rms=True, prenorm=prenorm,
+                       residual_in_fp32=residual_in_fp32)
+
+
+def layer_norm_fn(x, weight, bias, residual=None, eps=1e-6, prenorm=False, residual_in_fp32=False,
+                  is_rms_norm=False):
+    return CF.add_norm(x, weight, bias, residual=residual, eps=eps, is_rms=is_rms_norm, prenorm=prenorm,
+                       residual_in_fp32=residual_in_fp32)
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-5, device=None, dtype=None):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+        self.register_parameter("bias", None)
+
+    def forward(self, x, residual=None, prenorm=False, residual_in_fp32=False):
+        return rms_norm_fn(x, self.weight, self.bias, residual=residual, eps=self.eps, prenorm=prenorm,
+                           residual_in_fp32=residual_in_fp32)
+
+
+# =====================================================================================================
+# Mamba (one direction) — parameters and init identical to upstream
+# =====================================================================================================
+class Mamba(nn.Module):
+    def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
+                 dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, conv_bias=True, bias=False,
+                 use_fast_path=True, layer_idx=None, device=None, dtype=None):
+        super().__init__()
+        fk = {"device": device, "dtype": dtype}
+        self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else int(dt_rank)
+        self.use_fast_path, self.layer_idx = use_fast_path, layer_idx
+        if d_conv > 4:
+            raise NotImplementedError("caduceus_b200: d_conv must be <= 4 (as upstream causal_conv1d)")
+
+        self.in_proj = nn.Linear(d_model, 2 * self.d_inner, bias=bias, **fk)
+        self.conv1d = nn.Conv1d(self.d_inner, self.d_inner, kernel_size=d_conv, groups=self.d_inner,
+                                padding=d_conv - 1, bias=conv_bias, **fk)
+        self.activation = "silu"
+        self.act = nn.SiLU()
+        self.x_proj = nn.Linear(self.d_inner, self.dt_rank + 2 * d_state, bias=False, **fk)
+        self.dt_proj = nn.Linear(self.dt_rank, self.d_inner, bias=True, **fk)
+
+        std = self.dt_rank ** -0.5 * dt_scale
+        if dt_init == "constant":
+            nn.init.constant_(self.dt_proj.weight, std)
+        elif dt_init == "random":
+            nn.init.uniform_(self.dt_proj.weight, -std, std)
+        else:
+            raise NotImplementedError(f"dt_init={dt_init}")
+        # bias = softplus^-1(dt), dt log-uniform in [dt_min, dt_max]
+        dt = torch.exp(torch.rand(self.d_inner, **fk) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min))
+        dt = dt.clamp(min=dt_init_floor)
+        with torch.no_grad():
+            self.dt_proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))
+        self.dt_proj.bias._no_reinit = True
+
+        A = torch.arange(1, d_state + 1, dtype=torch.float32, device=device).repeat(self.d_inner, 1)
+        self.A_log = nn.Parameter(torch.log(A))
+        self.A_log._no_weight_decay = True
+        self.D = nn.Parameter(torch.ones(self.d_inner, device=device))
+        self.D._no_weight_decay = True
+        self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias, **fk)
+
+    def forward(self, hidden_states, inference_params=None):
+        if inference_params is not None:
+            raise NotImplementedError("caduceus_b200: step-wise decoding (inference_params) is outside the hot path")
+        return bimamba_inner(hidden_states, self, None, strategy=None, nstrand=1)
+
+    def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):
+        raise NotImplementedError("caduceus_b200: step-wise decoding is outside the hot path")
+
+
+class Block(nn.Module):
+    """Add -> Norm -> Mixer (upstream `Block`); returns (hidden, residual)."""
+
+    def __init__(self, dim, mixer_cls, norm_cls=nn.LayerNorm, fused_add_norm=False, residual_in_fp32=False):
+        super().__init__()
+        self.residual_in_fp32 = residual_in_fp32
+        self.fused_add_norm = fused_add_norm
+        self.mixer = mixer_cls(dim)
+        self.norm = norm_cls(dim)
+        if fused_add_norm and not isinstance(self.norm, (nn.LayerNorm, RMSNorm)):
+            raise AssertionError("Only LayerNorm and RMSNorm are supported for fused_add_norm")
+
+    def forward(self, hidden_states, residual=None, inference_params=None):
+        is_rms = isinstance(self.norm, RMSNorm)
+        if not self.fused_add_norm:
+            # upstream adds in the promoted dtype, stores that sum, and norms its cast to the weight dtype
+            residual = (hidden_states + residual) if residual is not None else hidden_states
+            hidden_states = CF.add_norm(residual.to(dtype=self.norm.weight.dtype), self.norm.weight, self.norm.bias,
+                                        eps=self.norm.eps, is_rms=is_rms)
+            if self.residual_in_fp32:
+                residual = residual.to(torch.float32)
+        else:
+            hidden_states, residual = CF.add_norm(
+                hidden_states, self.norm.weight, self.norm.bias, residual=residual, eps=self.norm.eps, is_rms=is_rms,
+                prenorm=True, residual_in_fp32=self.residual_in_fp32)
+        hidden_states = self.mixer(hidden_states, inference_params=inference_params)
+        return hidden_states, residual
+
+    def allocate_inference_cache(self, batch_size, max_seqlen, dtype=None, **kwargs):
+        return self.mixer.allocate_inference_cache(batch_size, max_seqlen, dtype=dtype, **kwargs)
+
+
+# =====================================================================================================
+# fused BiMamba inner path
+# =====================================================================================================
+def pack_scan_params(dirs):
+    """Stack per-direction scan parameters in the layout of cad_scan_fwd_args (fp32, differentiable)."""
+    conv_w4 = torch.stack([F.pad(m.conv1d.weight.float().squeeze(1), (4 - m.d_conv, 0)) for m in dirs])
+    conv_b = torch.stack([m.conv1d.bias.float() if m.conv1d.bias is not None
+                          else torch.zeros(m.d_inner, device=m.A_log.device) for m in dirs])
+    dt_w = torch.stack([m.dt_proj.weight.float() for m in dirs])
+    dt_b = torch.stack([m.dt_proj.bias.float() for m in dirs])
+    A2 = torch.stack([-torch.exp(m.A_log.float()) * _LOG2E for m in dirs])
+    Dk = torch.stack([m.D.float() for m in dirs])
+    return tuple(t.contiguous() for t in (conv_w4, conv_b, dt_w, dt_b, A2, Dk))
+
+
+class _DerivedCache:
+    """Inference-time cache of derived weights (flips / stacks / casts), invalidated by parameter versions."""
+
+    def __init__(self):
+        self.store = {}
+
+    def get(self, owner, params, tag, build):
+        key = (id(owner), tag)
+        sig = tuple((p.data_ptr(), p._version, p.dtype) for p in params if p is not None)
+        hit = self.store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = build()
+        self.store[key] = (sig, val)
+        return val
+
+
+_CACHE = _DerivedCache()
+
+
+def _act_dtype(hidden):
+    if torch.is_autocast_enabled():
+        return torch.get_autocast_dtype("cuda")
+    return hidden.dtype
+
+
+def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_ctx=None):
+    """BiMambaWrapper.forward (ref:caduceus/modeling_caduceus.py:122-140) — and, with nstrand=2, the whole
+    RCPSWrapper(BiMambaWrapper) of ref:caduceus/modeling_rcps.py:85-99 — as one fused pipeline:
+
+        in_proj GEMM (once per strand when the projections are tied)  ->  conv+SiLU  ->  x_proj GEMM  ->
+        ONE fused scan launch over all (batch, strand, direction) jobs  ->  out_proj GEMM (directions
+        concatenated along K when tied + "add").
+
+    hidden: (B, L, nstrand * D).  Strand 1 is consumed channel-reversed and time-reversed by
+    using column-/row-flipped projection weights and reversed scan jobs — no activation is ever flipped.
+    """
+    CF._require_cuda(hidden)
+    dirs = [mamba_fwd] + ([mamba_rev] if mamba_rev is not None else [])
+    ndir = len(dirs)
+    m0 = dirs[0]
+    B, L, width = hidden.shape
+    D = width // nstrand
+    assert D == m0.d_model, f"hidden width {width} != nstrand * d_model ({nstrand} * {m0.d_model})"
+    E, N, R = m0.d_inner, m0.d_state, m0.dt_rank
+    act = _act_dtype(hidden)
+    if hidden.dtype != act:
+        hidden = hidden.to(act)
+    if hidden.stride(-1) != 1:
+        hidden = hidden.contiguous()
+    dev = hidden.device
+    grad = torch.is_grad_enabled() and (hidden.requires_grad or any(p.requires_grad for m in dirs for p in m.parameters()))
+    if grad:
+        raise NotImplementedError("caduceus_b200: backward of the fused scan is not wired yet")
+
+    tied_in = ndir == 1 or (dirs[1].in_proj.weight is dirs[0].in_proj.weight and dirs[1].in_proj.bias is dirs[0].in_proj.bias)
+    tied_out = ndir == 1 or (dirs[1].out_proj.weight is dirs[0].out_proj.weight and dirs[1].out_proj.bias is dirs[0].out_proj.bias)
+    nw = 1 if tied_in else ndir
+    jobs = CF.job_tables(B, nstrand, ndir, not tied_in, dev)
+    Lp = CF.round_up(max(L, 1), 16)
+
+    # ---- derived weights -----------------------------------------------------------------------------
+    all_params = [p for m in dirs for p in m.parameters()]
+
+    def build():
+        d = {}
+        # in_proj per (strand, weight set): strand 1 reads the D input channels in reverse order
+        d["w_in"] = [[(dirs[w].in_proj.weight if s == 0 else dirs[w].in_proj.weight.flip(1)).to(act).contiguous()
+                      for w in range(nw)] for s in range(nstrand)]
+        d["b_in"] = [None if dirs[w].in_proj.bias is None else dirs[w].in_proj.bias.to(act) for w in range(nw)]
+        d["w_x"] = torch.stack([m.x_proj.weight.to(act) for m in dirs])                  # (P, R+2N, E)
+        d["packed"] = pack_scan_params(dirs)
+        # out_proj per (strand, direction): strand 1 writes the D output channels in reverse order
+        w_out = [[(m.out_proj.weight if s == 0 else m.out_proj.weight.flip(0)).to(act) for m in dirs]
+                 for s in range(nstrand)]
+        if tied_out and (ndir == 1 or strategy == "add"):
+            d["w_out_cat_t"] = [torch.cat(w_out[s], dim=1).t().contiguous() for s in range(nstrand)]   # (ndir*E, D)
+        else:
+            d["w_out_t"] = [[w.t().contiguous() for w in w_out[s]] for s in range(nstrand)]            # (E, D)
+        d["b_out"] = [[None if m.out_proj.bias is None else
+                       (m.out_proj.bias if s == 0 else m.out_proj.bias.flip(0)).to(act) for m in dirs]
+                      for s in range(nstrand)]
+        return d
+
+    dw = _CACHE.get(m0, all_params, ("bimamba", nstrand, ndir, str(act), strategy), build)
+    packed = dw["packed"]
+
+    # ---- in_proj: xz[b, s, w] = W_in[s][w] @ h[b, :, sD:(s+1)D]^T  -> (2E, L), channel-major ------------
+    xz = torch.empty(B, nstrand, nw, 2 * E, Lp, device=dev, dtype=act)
+    for s in range(nstrand):
+        hT = hidden[:, :, s * D:(s + 1) * D].transpose(1, 2)            # (B, D, L) view
+        for w in range(nw):
+            dst = xz[:, s, w, :, :L]
+            if B == 1:
+                torch.mm(dw["w_in"][s][w], hT[0], out=dst[0])
+            else:
+                torch.matmul(dw["w_in"][s][w], hT, out=dst)
+            if dw["b_in"][w] is not None:
+                dst += dw["b_in"][w][None, :, None]
+    xz = xz.view(B * nstrand * nw, 2 * E, Lp)
+
+    # ---- conv + SiLU, x_proj GEMM ----------------------------------------------------------------------
+    halo = None if seq_ctx is None else seq_ctx.get("halo")
+    u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                        # (njobs, E, Lp)
+    wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
+    xdbl = torch.bmm(wx_job, u)                                                           # (njobs, R+2N, Lp)
+    del u
+
+    # ---- fused scan --------------------------------------------------------------------------------------
+    h0 = None if seq_ctx is None else seq_ctx.get("h0")
+    want_state = seq_ctx is not None and seq_ctx.get("want_state", False)
+    yg, hlast, dtsum, _ = CF.scan_fwd(xz, xdbl, packed, jobs, L, halo=halo, h0=h0, want_state=want_state)
+    if want_state:
+        seq_ctx["hlast"], seq_ctx["dtsum"] = hlast, dtsum
+        seq_ctx["xdbl"], seq_ctx["packed"], seq_ctx["jobs"] = xdbl, packed, jobs
+    del xz
+
+    # ---- out_proj -------------------------------------------------------------------------------------------
+    out = torch.empty(B, L, width, device=dev, dtype=act)
+    yg = yg.view(B, nstrand, ndir, E, Lp)
+    for s in range(nstrand):
+        for b in range(B):
+            dst = out[b, :, s * D:(s + 1) * D]
+            if "w_out_cat_t" in dw:
+                a_t = yg[b, s].reshape(ndir * E, Lp)[:, :L].t()                           # (L, ndir*E) view
+                torch.mm(a_t, dw["w_out_cat_t"][s], out=dst)
+                bias = dw["b_out"][s][0]
+                if bias is not None:
+                    dst += bias * ndir
+            else:
+                parts = []
+                for d in range(ndir):
+                    o = torch.mm(yg[b, s, d, :, :L].t(), dw["w_out_t"][s][d])
+                    if dw["b_out"][s][d] is not None:
+                        o = o + dw["b_out"][s][d]
+                    parts.append(o)
+                if ndir == 1:
+                    dst.copy_(parts[0])
+                elif strategy == "add":
+                    torch.add(parts[0], parts[1], out=dst)
+                elif strategy == "ew_multiply":
+                    torch.mul(parts[0], parts[1], out=dst)
+                else:
+                    raise NotImplementedError(f"`{strategy}` for bi-directionality not implemented!")
+    return out

@@ -1,0 +1,166 @@
+/*
+ * caduceus_b200 — C-ABI of the B200-native (sm_100a) kernels behind Caduceus' bidirectional selective-SSM
+ * hot path.  Plain C: device pointers, sizes, strides, enums.  No torch / ATen types.
+ *
+ * What this boundary replaces (SURVEY.md §8b "B-native").  The reference (kuleshov-group/caduceus) holds no
+ * native code of its own; its hot path calls the pybind entry points of two un-vendored CUDA extensions,
+ * reached through these reference call sites:
+ *
+ *   selective_scan_cuda.fwd / .bwd      <- mamba_ssm.Mamba.forward  <- ref:caduceus/modeling_caduceus.py:105-113,128-133
+ *   causal_conv1d_cuda.causal_conv1d_fwd/_bwd  (same call chain)
+ *   Triton _layer_norm_fwd/_bwd         <- rms_norm_fn/layer_norm_fn <- ref:caduceus/modeling_caduceus.py:244-273,
+ *                                                                       ref:caduceus/modeling_rcps.py:177-195
+ *   torch index ops (flip/gather/cat)   <- RCPSEmbedding.forward     <- ref:caduceus/modeling_rcps.py:46-67
+ *
+ * Conventions
+ *   - Every function returns 0 on success, <0 for an argument/shape error (text via cad_last_error()),
+ *     >0 = the cudaError_t of a failed launch.  No C++ exceptions cross the boundary.
+ *   - The library never allocates or frees device memory and never synchronises the device.  All work is
+ *     enqueued on the `stream` argument (a cudaStream_t passed as void*).
+ *   - The caller (PyTorch) owns every buffer and keeps it alive until the stream reaches the call.
+ *   - All "time-major rows" are contiguous along the sequence axis; `ld*` arguments are row pitches in ELEMENTS.
+ *     Fast (128-bit) paths need 16-byte aligned base pointers and pitches; otherwise a scalar path is used.
+ */
+#ifndef CADUCEUS_B200_H_
+#define CADUCEUS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAD_ABI_VERSION 1
+
+typedef enum { CAD_F32 = 0, CAD_F16 = 1, CAD_BF16 = 2 } cad_dtype;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int         cad_version(void);            /* == CAD_ABI_VERSION */
+const char* cad_last_error(void);         /* thread-local message of the last <0 return */
+int         cad_sm_count(void);           /* multiprocessors of the current device (cached) */
+
+/* ---- token embedding, Ph and RC-equivariant PS (ref:caduceus/modeling_caduceus.py:159-163,
+ *      ref:caduceus/modeling_rcps.py:46-67).  Integer index work, bit-exact:
+ *        out[b, l, c]     = W[ids[b, l], c]                     c in [0, D)
+ *        out[b, l, D + c] = W[cmap[ids[b, l]], D - 1 - c]       (only if rcps)
+ *      which equals cat[emb(ids), flip_{L,C}(emb(cmap[flip_L(ids)]))].                                   */
+typedef struct {
+  const int64_t* ids;      /* (B, L) token ids */
+  const void*    weight;   /* (V, D) embedding table, dtype `dtype` */
+  const int64_t* cmap;     /* (V) complement map, or NULL when !rcps */
+  void*          out;      /* (B, L, D) or (B, L, 2D) */
+  int64_t B, L, V, D;
+  int32_t rcps;
+  int32_t dtype;           /* cad_dtype of weight/out */
+} cad_embedding_args;
+int cad_embedding_fwd(const cad_embedding_args* a, void* stream);
+
+/* gradient of the table: dW[v, c] += sum over (b,l) with ids==v of dout[b,l,c]  (+ RC half, same index map).
+ * dW must be zero-initialised fp32 (V, D). */
+typedef struct {
+  const int64_t* ids; const int64_t* cmap; const void* dout; float* dweight;
+  int64_t B, L, V, D; int32_t rcps; int32_t dtype;
+} cad_embedding_bwd_args;
+int cad_embedding_bwd(const cad_embedding_bwd_args* a, void* stream);
+
+/* ---- fused residual-add + RMSNorm / LayerNorm (replaces rms_norm_fn / layer_norm_fn).
+ *      Rows are (token, half) pairs; `nhalf` = 1 (Ph) or 2 (PS, hidden has 2*D channels).
+ *      For half h of token row r:
+ *         v   = x[r, in_half(h)*D : +D] (+ residual[r, in_half(h)*D : +D])          in fp32
+ *         res_out[r, h*D : +D] = v                                                 (if res_out != NULL)
+ *         y[r, h*D : +D]       = norm(v) * w' (+ b'),   w' = weight or reversed(weight) per `wflip_mask`
+ *      in_half(h) = h ^ swap.  The literal half swap of the reference's fused RCPS block
+ *      (ref:caduceus/modeling_rcps.py:177-197) is swap=1, wflip_mask=0b10; its non-fused
+ *      block and the final norm (ref:caduceus/modeling_caduceus.py:242-262) are swap=0, wflip_mask=0b10.    */
+typedef struct {
+  const void* x;          /* (rows, nhalf*D), pitch ldx */
+  const void* residual;   /* same shape, pitch ldr, dtype res_in_dtype; may be NULL */
+  const void* weight;     /* (D) dtype wdtype */
+  const void* bias;       /* (D) or NULL */
+  void*       y;          /* (rows, nhalf*D) pitch ldy, dtype xdtype */
+  void*       res_out;    /* (rows, nhalf*D) pitch ldo, dtype res_out_dtype; may be NULL */
+  float*      rstd;       /* (rows, nhalf) saved 1/sigma for backward, or NULL */
+  float*      mean;       /* (rows, nhalf) saved mean (LayerNorm only), or NULL */
+  int64_t rows, D, ldx, ldr, ldy, ldo;
+  int32_t nhalf, swap, wflip_mask, is_rms;
+  int32_t xdtype, wdtype, res_in_dtype, res_out_dtype;
+  float   eps;
+} cad_add_norm_args;
+int cad_add_norm_fwd(const cad_add_norm_args* a, void* stream);
+
+/* backward of the above.  dy: grad of y; dres_out: grad flowing into res_out (may be NULL).
+ * Outputs: dx (grad of x == grad of residual, written once; caller aliases), dweight/dbias partial sums
+ * (nblocks, D) fp32 to be summed by the caller (deterministic two-stage reduction). */
+typedef struct {
+  const void* dy; const void* dres_out; const void* v /* saved res_out (or x when no residual) */;
+  const void* weight; const float* rstd; const float* mean;
+  void* dx; float* dweight_partial; float* dbias_partial;
+  int64_t rows, D, lddy, lddr, ldv, lddx;
+  int32_t nhalf, swap, wflip_mask, is_rms, has_bias;
+  int32_t dydtype, vdtype, wdtype, dxdtype, drdtype;
+  int32_t nblocks;
+} cad_add_norm_bwd_args;
+int cad_add_norm_bwd(const cad_add_norm_bwd_args* a, void* stream);
+int cad_add_norm_bwd_blocks(int64_t rows);   /* nblocks the backward wants for `rows` */
+
+/* ---- BiMamba inner path: (anti)causal depthwise conv + SiLU, dt/B/C, selective scan, gate.
+ *      Replaces causal_conv1d_fwd + selective_scan_cuda.fwd (and the two flips + second Mamba of
+ *      ref:caduceus/modeling_caduceus.py:128-137; the RC strand of ref:caduceus/modeling_rcps.py:85-99).
+ *
+ *  A "job" j = (sequence s, direction p): one Mamba run over one sequence in one physical direction.
+ *      xz      (nseq, 2E, ldxz)     in-proj output, channel-major; rows [0,E) = x, [E,2E) = z
+ *      xdbl    (njobs, R+2N, ldxd)  x_proj output of job j: rows [0,R) dt low-rank, [R,R+N) B, [R+N,R+2N) C
+ *      out     (njobs, E, ldo)      gated scan output  y * silu(z)   (pre out_proj)
+ *  job j uses sequence  seq_of_job[j], parameter set  pset_of_job[j]  (0 = mamba_fwd, 1 = mamba_rev) and runs
+ *  right-to-left in physical time iff  rev_of_job[j].  Parameter sets are packed fp32:
+ *      conv_w (P, E, 4) taps zero-padded at the front to 4;  conv_b (P, E);  dt_w (P, E, R);  dt_b (P, E);
+ *      A2 (P, E, N) = -exp(A_log) * log2(e);  Dskip (P, E).
+ *  Semantics in LOGICAL time tau (tau = t, or L-1-t when reversed), SURVEY.md A.1/A.2/A.5:
+ *      u[tau]  = silu(conv_b + sum_k conv_w[k] * x[tau-3+k])
+ *      dt[tau] = softplus(dt_b + dt_w . xdbl[0:R, tau])      (threshold 20)
+ *      h[tau]  = exp2(dt*A2) * h[tau-1] + dt*B[tau]*u[tau],  h[-1] = h0 (or 0)
+ *      y[tau]  = C[tau] . h[tau] + Dskip*u[tau];    out = y * silu(z)
+ *  Optional sequence-sharding hooks: conv halo in, carry-state in, and per-job outputs
+ *  (sum of dt per channel, final state) so that a shard can be composed with its neighbours.               */
+typedef struct {
+  const void*  xz;
+  const void*  xdbl;
+  void*        out;
+  const float* conv_w; const float* conv_b; const float* dt_w; const float* dt_b;
+  const float* A2;     const float* Dskip;
+  const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;   /* device, (njobs) */
+  /* sharding hooks, all optional (NULL): */
+  const void*  halo;        /* (njobs, E, 3) x values preceding logical time 0, dtype io */
+  const float* h0;          /* (njobs, E, N) carry-in state */
+  float*       hlast;       /* (njobs, E, N) final state (with h0 folded in) */
+  float*       dtsum;       /* (njobs, E) sum over tau of dt */
+  /* optional saved tensors for backward (NULL in inference): */
+  float*       chunk_state; /* (njobs, E, nchunks, N) state at the END of each 512-token logical chunk */
+  int64_t L, E, N, R, K;
+  int64_t ldxz, ldxd, ldo;
+  int32_t nseq, njobs, npset;
+  int32_t io_dtype;         /* dtype of xz / xdbl / out / halo */
+  int32_t channels_per_cta; /* 0 = library picks so that the grid is ~ a multiple of the SM count */
+} cad_scan_fwd_args;
+int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
+int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
+
+/* v1 helper: u = silu(conv(x)) materialised per job for the x_proj GEMM  (njobs, E, ldu). */
+typedef struct {
+  const void* xz; void* u;
+  const float* conv_w; const float* conv_b;
+  const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;
+  const void* halo;
+  int64_t L, E, ldxz, ldu;
+  int32_t nseq, njobs, io_dtype;
+} cad_conv_fwd_args;
+int cad_conv_silu_fwd(const cad_conv_fwd_args* a, void* stream);
+
+/* ---- micro-benchmarks of the pipes that bound the scan (MUFU ex2, FFMA), used by bench.py to quote
+ *      "fraction of measured MUFU peak" beside the HBM fraction.  Writes ops/s.          */
+int cad_microbench(int which /*0 = ex2.approx.f32, 1 = ffma, 2 = ex2+4ffma mix*/, double* ops_per_s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* CADUCEUS_B200_H_ */
