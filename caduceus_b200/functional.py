@@ -13,6 +13,14 @@ from ._lib import CAD_BF16, CAD_F16, CAD_F32
 
 _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 
+LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
+SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
+
+
+def _launched(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _dt(t):
     try:
@@ -72,6 +80,7 @@ class _EmbeddingFn(torch.autograd.Function):
         out = torch.empty(B, L, 2 * D if rcps else D, device=w.device, dtype=w.dtype)
         a = _lib.EmbeddingArgs(_ptr(ids), _ptr(w), _ptr(cmap), _ptr(out), B, L, V, D, int(rcps), _dt(w))
         _lib.check(lib.cad_embedding_fwd(C.byref(a), _stream()), "cad_embedding_fwd")
+        _launched()
         ctx.save_for_backward(ids, cmap)
         ctx.shape = (V, D, w.dtype)
         return out
@@ -87,6 +96,7 @@ class _EmbeddingFn(torch.autograd.Function):
         a = _lib.EmbeddingBwdArgs(_ptr(ids), _ptr(cmap), _ptr(dout), _ptr(dw), B, L, V, D, int(cmap is not None),
                                   _dt(dout))
         _lib.check(lib.cad_embedding_bwd(C.byref(a), _stream()), "cad_embedding_bwd")
+        _launched()
         return None, dw.to(wdtype), None
 
 
@@ -128,6 +138,7 @@ class _AddNormFn(torch.autograd.Function):
             rows, D, ldx, ldr, width, width, nhalf, swap, wflip_mask, int(is_rms),
             _dt(x2), _dt(w), _dt(r2) if r2 is not None else CAD_F32, _DT[res_dtype], float(eps))
         _lib.check(lib.cad_add_norm_fwd(C.byref(a), _stream()), "cad_add_norm_fwd")
+        _launched()
         if needs_grad:
             ctx.save_for_backward(res_out, w, rstd, mean)
             ctx.meta = (rows, D, width, nhalf, swap, wflip_mask, is_rms, b is not None, x.dtype,
@@ -159,6 +170,7 @@ class _AddNormFn(torch.autograd.Function):
             rows, D, lddy, lddr, width, width, nhalf, swap, wflip_mask, int(is_rms), int(has_bias),
             _dt(dy2), _dt(res_out), _dt(w), _DT[gdtype], _dt(dr2) if dr2 is not None else CAD_F32, nblocks)
         _lib.check(lib.cad_add_norm_bwd(C.byref(a), _stream()), "cad_add_norm_bwd")
+        _launched()
         dw = dwp.sum(0).to(wdtype)
         db = dbp.sum(0).to(bdtype) if has_bias else None
         gx = dx if dx.dtype == xdtype else dx.to(xdtype)
@@ -223,6 +235,7 @@ def conv_silu(xz, conv_w4, conv_b, jobs, L, halo=None):
     a = _lib.ConvFwdArgs(_ptr(xz), _ptr(u), _ptr(conv_w4), _ptr(conv_b), _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo),
                          L, E, ld, ld, nseq, njobs, _dt(xz))
     _lib.check(lib.cad_conv_silu_fwd(C.byref(a), _stream()), "cad_conv_silu_fwd")
+    _launched()
     return u
 
 
@@ -249,7 +262,15 @@ def scan_fwd(xz, xdbl, packed, jobs, L, *, halo=None, h0=None, want_state=False,
         _ptr(xz), _ptr(xdbl), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_w), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
         L, E, N, R, 4, ldxz, ldxd, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta)
+    ev = None
+    if SCAN_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _lib.check(lib.cad_bimamba_scan_fwd(C.byref(a), _stream()), "cad_bimamba_scan_fwd")
+    _launched()
+    if ev is not None:
+        ev[1].record()
+        SCAN_EVENTS.append(ev)
     return out, hlast, dtsum, cstate
 
 

@@ -69,6 +69,9 @@ def make_model_fixture(ref, tag, *, d_model, n_layer, seqlen, bsz, rcps, fused_a
     ids = hg38_ids(bsz, seqlen, gen)
     with torch.no_grad():
         out = model(ids, output_hidden_states=True, return_dict=True)
+        # NB the reference appends the final normed state to hidden_states only in its fused branch
+        # (ref:caduceus/modeling_caduceus.py:274-275), so take last_hidden_state from the backbone itself
+        last = model.caduceus(ids, return_dict=True).last_hidden_state
     fx = {
         "config": dict(d_model=d_model, n_layer=n_layer, vocab_size=12, ssm_cfg=dict(SSM_CFG), rms_norm=rms_norm,
                        fused_add_norm=fused_add_norm, residual_in_fp32=residual_in_fp32,
@@ -78,7 +81,7 @@ def make_model_fixture(ref, tag, *, d_model, n_layer, seqlen, bsz, rcps, fused_a
         "state_dict": {k: v.clone() for k, v in model.state_dict().items()},
         "input_ids": ids,
         "logits": out.logits.clone(),
-        "last_hidden_state": out.hidden_states[-1].clone(),
+        "last_hidden_state": last.clone(),
         "hidden_after_embedding": out.hidden_states[0].clone(),
     }
     path = os.path.join(OUT, f"model_{tag}.pt")

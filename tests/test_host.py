@@ -1,0 +1,128 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, the drop-in API surface
+(class names, state_dict keys, config fields, tokenizer ids), and loud failure without CUDA."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, golden
+import caduceus
+import caduceus_b200
+from caduceus_b200 import _lib
+from caduceus_b200 import functional as CF
+
+
+def test_header_symbols_are_exported_and_bound():
+    header = open(os.path.join(ROOT, "include", "caduceus_b200.h")).read()
+    declared = set(re.findall(r"\b(cad_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cad_dtype"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    if not os.path.exists(_lib.LIB_PATH):
+        from caduceus_b200.build import build
+        build()
+    lib = _lib.load()                      # getattr on every symbol happens inside load()
+    assert lib.cad_version() == _lib.ABI_VERSION
+    assert lib.cad_scan_chunk_len() == 512
+
+
+def test_struct_sizes_match_header_layout():
+    # field counts guard against silent drift between include/caduceus_b200.h and the ctypes mirror
+    header = open(os.path.join(ROOT, "include", "caduceus_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    structs = {m.group(2): m.group(1) for m in re.finditer(r"typedef struct \{([^}]*)\}\s*(\w+);", header)}
+    for cname, cls in (("cad_embedding_args", _lib.EmbeddingArgs), ("cad_add_norm_args", _lib.AddNormArgs),
+                       ("cad_scan_fwd_args", _lib.ScanFwdArgs), ("cad_conv_fwd_args", _lib.ConvFwdArgs),
+                       ("cad_add_norm_bwd_args", _lib.AddNormBwdArgs), ("cad_embedding_bwd_args", _lib.EmbeddingBwdArgs)):
+        names = []
+        for decl in structs[cname].split(";"):
+            for part in decl.split(","):
+                found = re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())
+                if found:
+                    names.append(found[0])
+        assert names == [f[0] for f in cls._fields_], (cname, names, [f[0] for f in cls._fields_])
+
+
+def test_cpu_tensors_fail_loudly():
+    m = caduceus_b200.BiMambaWrapper(32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 8, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CF.add_norm(torch.randn(4, 32), torch.ones(32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CF.embedding(torch.zeros(1, 4, dtype=torch.long), torch.randn(16, 32))
+
+
+@pytest.mark.parametrize("tag", ["ph_config0", "ps_config0", "ps_nonfused", "ph_nonfused_ln", "ph_mul_untied", "ph_unidir"])
+def test_state_dict_keys_and_shapes_match_reference(tag):
+    fx = golden(f"model_{tag}.pt")
+    cfg = caduceus.CaduceusConfig(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in fx["config"].items()})
+    model = caduceus.CaduceusForMaskedLM(cfg)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(fx["state_dict"].keys())
+    for k, v in sd.items():
+        assert v.shape == fx["state_dict"][k].shape and v.dtype == fx["state_dict"][k].dtype, k
+    model.load_state_dict(fx["state_dict"])
+    lm, emb = model.lm_head.weight, model.get_input_embeddings().weight
+    assert lm.data_ptr() == emb.data_ptr()          # tied (PS always; Ph under the reference's transformers pin)
+
+
+def test_init_statistics_follow_reference_init():
+    cfg = caduceus.CaduceusConfig(d_model=128, n_layer=4, vocab_size=12, ssm_cfg={"d_state": 16},
+                                  initializer_cfg={"initializer_range": 0.02, "rescale_prenorm_residual": True,
+                                                   "n_residuals_per_layer": 1})
+    m = caduceus.CaduceusForMaskedLM(cfg)
+    mf = m.caduceus.backbone.layers[0].mixer.mamba_fwd
+    assert torch.allclose(mf.A_log[0, :3], torch.log(torch.tensor([1.0, 2.0, 3.0])))
+    assert torch.all(mf.D == 1) and mf.A_log._no_weight_decay and mf.D._no_weight_decay
+    dt = torch.nn.functional.softplus(mf.dt_proj.bias)
+    assert dt.min() >= 1e-4 and dt.max() <= 0.1001 and mf.dt_proj.bias._no_reinit
+    assert m.config.vocab_size == 16
+    assert abs(mf.out_proj.weight.std().item() - (1 / (3 * 256) ** 0.5) / 2) < 0.01
+    mr = m.caduceus.backbone.layers[0].mixer.mamba_rev
+    assert mr.in_proj.weight is mf.in_proj.weight and mr.out_proj.weight is mf.out_proj.weight
+    assert mr.x_proj.weight is not mf.x_proj.weight
+
+
+def test_tokenizer_ids_and_complement_map():
+    tok = caduceus.CaduceusTokenizer(model_max_length=32)
+    assert tok.get_vocab() == {"[CLS]": 0, "[SEP]": 1, "[BOS]": 2, "[MASK]": 3, "[PAD]": 4, "[RESERVED]": 5,
+                               "[UNK]": 6, "A": 7, "C": 8, "G": 9, "T": 10, "N": 11}
+    assert list(tok.complement_map.values()) == [0, 1, 2, 3, 4, 5, 6, 10, 9, 8, 7, 11]
+    assert tok("acgtn", add_special_tokens=False)["input_ids"] == [7, 8, 9, 10, 11]
+    assert tok("AC")["input_ids"] == [7, 8, 1]
+
+
+def test_config_roundtrip_and_auto_registration(tmp_path):
+    from transformers import AutoConfig
+    cmap = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 6, 7: 10, 8: 9, 9: 8, 10: 7, 11: 11}
+    cfg = caduceus.CaduceusConfig(d_model=64, n_layer=2, vocab_size=12, rcps=True, complement_map=cmap)
+    cfg.save_pretrained(tmp_path)
+    back = AutoConfig.from_pretrained(tmp_path)
+    assert isinstance(back, caduceus.CaduceusConfig) and back.model_type == "caduceus"
+    assert list(back.complement_map.values()) == list(cmap.values()) and back.rcps and back.d_model == 64
+    for f in ("ssm_cfg", "rms_norm", "residual_in_fp32", "fused_add_norm", "pad_vocab_size_multiple", "norm_epsilon",
+              "initializer_cfg", "bidirectional", "bidirectional_strategy", "bidirectional_weight_tie"):
+        assert hasattr(back, f)
+
+
+def test_rcps_lm_head_single_gemm_equals_reference_formula():
+    from caduceus_b200.modeling_rcps import RCPSLMHead
+    torch.manual_seed(0)
+    cmap = {i: i for i in range(16)}
+    cmap.update({7: 10, 10: 7, 8: 9, 9: 8})
+    head = RCPSLMHead(true_dim=24, vocab_size=16, complement_map=cmap)
+    x = torch.randn(2, 9, 48)
+    w = head.weight
+    ref = torch.nn.functional.linear(x[..., :24], w) + torch.nn.functional.linear(
+        torch.flip(x[..., 24:], dims=[-1]), w[head.complement_map, :])
+    assert torch.allclose(head(x), ref, atol=1e-5)
+
+
+def test_job_tables():
+    seq, pset, rev = CF.job_tables(2, 2, 2, False, "cpu")
+    assert seq.tolist() == [0, 0, 1, 1, 2, 2, 3, 3]
+    assert pset.tolist() == [0, 1] * 4
+    assert rev.tolist() == [0, 1, 1, 0] * 2          # strand 1: mamba_fwd runs right-to-left, mamba_rev left-to-right
+    seq_u, _, _ = CF.job_tables(1, 1, 2, True, "cpu")
+    assert seq_u.tolist() == [0, 1]
