@@ -283,7 +283,9 @@ static int norm_grid(int64_t nrow, int threads) {
 
 extern "C" int cad_add_norm_fwd(const cad_add_norm_args* a, void* stream_) {
   using namespace cad;
-  CAD_REQUIRE(a && a->x && a->weight && a->y, "cad_add_norm_fwd: null pointer");
+  CAD_REQUIRE(a, "cad_add_norm_fwd: null argument block");
+  if (a->rows == 0) return 0;
+  CAD_REQUIRE(a->x && a->weight && a->y, "cad_add_norm_fwd: null pointer");
   CAD_REQUIRE(a->nhalf == 1 || a->nhalf == 2, "cad_add_norm_fwd: nhalf must be 1 or 2");
   CAD_REQUIRE(a->D > 0 && a->D % 8 == 0 && a->D <= 2048, "cad_add_norm_fwd: D (%lld) must be a multiple of 8, <= 2048",
               (long long)a->D);

@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(
 
 extern "C" int cad_embedding_fwd(const cad_embedding_args* a, void* stream_) {
   using namespace cad;
-  CAD_REQUIRE(a && a->ids && a->weight && a->out, "cad_embedding_fwd: null pointer");
+  CAD_REQUIRE(a, "cad_embedding_fwd: null argument block");
   CAD_REQUIRE(a->B >= 0 && a->L >= 0 && a->V > 0 && a->D > 0, "cad_embedding_fwd: bad sizes");
+  if (a->B * a->L == 0) return 0;           // empty batch: nothing to enqueue (pointers may be null)
+  CAD_REQUIRE(a->ids && a->weight && a->out, "cad_embedding_fwd: null pointer");
   CAD_REQUIRE(!a->rcps || a->cmap, "cad_embedding_fwd: rcps needs a complement map");
   const int64_t vec = 16 / (int64_t)dtype_size(a->dtype);
   CAD_REQUIRE(a->D % vec == 0, "cad_embedding_fwd: D (%lld) must be a multiple of %lld", (long long)a->D,
@@ -103,7 +105,9 @@ extern "C" int cad_embedding_fwd(const cad_embedding_args* a, void* stream_) {
 
 extern "C" int cad_embedding_bwd(const cad_embedding_bwd_args* a, void* stream_) {
   using namespace cad;
-  CAD_REQUIRE(a && a->ids && a->dout && a->dweight, "cad_embedding_bwd: null pointer");
+  CAD_REQUIRE(a, "cad_embedding_bwd: null argument block");
+  if (a->B * a->L == 0) return 0;
+  CAD_REQUIRE(a->ids && a->dout && a->dweight, "cad_embedding_bwd: null pointer");
   CAD_REQUIRE(!a->rcps || a->cmap, "cad_embedding_bwd: rcps needs a complement map");
   CAD_REQUIRE(a->V * a->D * 4 <= 48 * 1024, "cad_embedding_bwd: V*D too large for the smem tile");
   const int64_t rows = a->B * a->L;
