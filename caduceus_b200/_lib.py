@@ -45,12 +45,12 @@ class AddNormBwdArgs(C.Structure):
 
 
 class ScanFwdArgs(C.Structure):
-    _fields_ = [("xz", _p), ("xdbl", _p), ("out", _p),
-                ("conv_w", _p), ("conv_b", _p), ("dt_w", _p), ("dt_b", _p), ("A2", _p), ("Dskip", _p),
+    _fields_ = [("xz", _p), ("delta", _p), ("bc", _p), ("out", _p),
+                ("conv_w", _p), ("conv_b", _p), ("dt_b", _p), ("A2", _p), ("Dskip", _p),
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p),
                 ("halo", _p), ("h0", _p), ("hlast", _p), ("dtsum", _p), ("chunk_state", _p),
-                ("L", _i64), ("E", _i64), ("N", _i64), ("R", _i64), ("K", _i64),
-                ("ldxz", _i64), ("ldxd", _i64), ("ldo", _i64),
+                ("L", _i64), ("E", _i64), ("N", _i64), ("K", _i64),
+                ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
                 ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32)]
 
 

@@ -1,0 +1,86 @@
+// Shared pieces of the fused scan kernels (forward and backward): chunk geometry, mbarrier/TMA primitives,
+// the host-side tensor map over the B/C rows.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace cad {
+
+constexpr int kTok = 16;            // tokens per lane
+constexpr int kChunk = 32 * kTok;   // 512 logical tokens per chunk
+constexpr int kMaxG = 7;            // channels (warps) per CTA
+constexpr int kBlkTok = 32;         // tokens per 128-byte swizzle line
+
+// ---- mbarrier / TMA primitives ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(smem_u32(bar)) : "memory");
+}
+
+
+// this lane's four 16-byte pieces inside a TMA-swizzled tile row (see scan_fwd.cu): SWIZZLE_128B stores 16-byte
+// chunk c of 128-byte line l at chunk position c ^ (l & 7); a tile row is 16 consecutive lines.
+__device__ __forceinline__ void tile_piece_offsets(int seg, uint32_t (&poff)[4]) {
+  const int blk = seg >> 1, c0 = 4 * (seg & 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) poff[k] = blk * 128 + (((c0 + k) ^ (blk & 7)) << 4);
+}
+
+// ---- host: tensor map over a (nrows, ld) fp32 matrix viewed as (32 tokens, blocks, rows) ----------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rows_per_box rows x 512 tokens per TMA; blocks past ceil(L/32) are out of bounds -> zero-filled.
+inline int make_row_tile_map(CUtensorMap* tmap, const float* base, int64_t nrows, int64_t ld, int64_t L,
+                             int rows_per_box) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return -1; }
+  const cuuint64_t nblk = (cuuint64_t)((L + kBlkTok - 1) / kBlkTok);
+  const cuuint64_t dims[3] = {(cuuint64_t)kBlkTok, nblk, (cuuint64_t)nrows};
+  const cuuint64_t strides[2] = {(cuuint64_t)kBlkTok * 4, (cuuint64_t)ld * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kBlkTok, (cuuint32_t)(kChunk / kBlkTok), (cuuint32_t)rows_per_box};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+  return 0;
+}
+
+}  // namespace cad

@@ -239,18 +239,30 @@ def conv_silu(xz, conv_w4, conv_b, jobs, L, halo=None):
     return u
 
 
-def scan_fwd(xz, xdbl, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
+def project_dt_bc(xdbl, dt_w_job, L, N):
+    """From x_dbl (njobs, R+2N, ld): dt_raw = W_dt . x_dbl[:R] (a K=R GEMM, io dtype) and the fp32 B/C rows in
+    the TMA-friendly pitch (multiple of 32 tokens, zero padded)."""
+    njobs, rows, ld = xdbl.shape
+    R = rows - 2 * N
+    delta = torch.bmm(dt_w_job, xdbl[:, :R, :])                                   # (njobs, E, ld)
+    ldbc = round_up(max(L, 1), 32)
+    bc = torch.zeros(njobs, 2 * N, ldbc, device=xdbl.device, dtype=torch.float32)
+    bc[:, :, :L] = xdbl[:, R:, :L]
+    return delta, bc
+
+
+def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
              channels_per_cta=0):
-    """Launch the fused bidirectional scan.  xz (nseq, 2E, ld), xdbl (njobs, R+2N, ld) -> out (njobs, E, ld)."""
+    """Launch the fused bidirectional scan.
+    xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld)."""
     lib = _lib.load()
     seq, pset, rev = jobs
-    conv_w4, conv_b, dt_w, dt_b, A2, Dk = packed
+    conv_w4, conv_b, dt_b, A2, Dk = packed
     nseq, twoE, ldxz = xz.shape
     E = twoE // 2
-    njobs, rows, ldxd = xdbl.shape
+    njobs, twoN, ldbc = bc.shape
     P, _, N = A2.shape
-    R = dt_w.shape[-1]
-    assert rows == R + 2 * N
+    assert twoN == 2 * N and delta.shape[0] == njobs and delta.shape[1] == E
     out = torch.empty(njobs, E, ldxz, device=xz.device, dtype=xz.dtype)
     hlast = torch.empty(njobs, E, N, device=xz.device, dtype=torch.float32) if want_state else None
     dtsum = torch.empty(njobs, E, device=xz.device, dtype=torch.float32) if want_state else None
@@ -259,9 +271,9 @@ def scan_fwd(xz, xdbl, packed, jobs, L, *, halo=None, h0=None, want_state=False,
     cstate = (torch.empty(njobs, E, nchunks, N, device=xz.device, dtype=torch.float32)
               if want_chunk_state else None)
     a = _lib.ScanFwdArgs(
-        _ptr(xz), _ptr(xdbl), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_w), _ptr(dt_b), _ptr(A2), _ptr(Dk),
+        _ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
-        L, E, N, R, 4, ldxz, ldxd, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta)
+        L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta)
     ev = None
     if SCAN_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

@@ -140,11 +140,10 @@ def pack_scan_params(dirs):
     conv_w4 = torch.stack([F.pad(m.conv1d.weight.float().squeeze(1), (4 - m.d_conv, 0)) for m in dirs])
     conv_b = torch.stack([m.conv1d.bias.float() if m.conv1d.bias is not None
                           else torch.zeros(m.d_inner, device=m.A_log.device) for m in dirs])
-    dt_w = torch.stack([m.dt_proj.weight.float() for m in dirs])
     dt_b = torch.stack([m.dt_proj.bias.float() for m in dirs])
     A2 = torch.stack([-torch.exp(m.A_log.float()) * _LOG2E for m in dirs])
     Dk = torch.stack([m.D.float() for m in dirs])
-    return tuple(t.contiguous() for t in (conv_w4, conv_b, dt_w, dt_b, A2, Dk))
+    return tuple(t.contiguous() for t in (conv_w4, conv_b, dt_b, A2, Dk))
 
 
 class _DerivedCache:
@@ -191,7 +190,7 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
     B, L, width = hidden.shape
     D = width // nstrand
     assert D == m0.d_model, f"hidden width {width} != nstrand * d_model ({nstrand} * {m0.d_model})"
-    E, N, R = m0.d_inner, m0.d_state, m0.dt_rank
+    E, N = m0.d_inner, m0.d_state
     act = _act_dtype(hidden)
     if hidden.dtype != act:
         hidden = hidden.to(act)
@@ -218,6 +217,7 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
                       for w in range(nw)] for s in range(nstrand)]
         d["b_in"] = [None if dirs[w].in_proj.bias is None else dirs[w].in_proj.bias.to(act) for w in range(nw)]
         d["w_x"] = torch.stack([m.x_proj.weight.to(act) for m in dirs])                  # (P, R+2N, E)
+        d["w_dt"] = torch.stack([m.dt_proj.weight.to(act) for m in dirs])                # (P, E, R)
         d["packed"] = pack_scan_params(dirs)
         # out_proj per (strand, direction): strand 1 writes the D output channels in reverse order
         w_out = [[(m.out_proj.weight if s == 0 else m.out_proj.weight.flip(0)).to(act) for m in dirs]
@@ -254,14 +254,16 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
     wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
     xdbl = torch.bmm(wx_job, u)                                                           # (njobs, R+2N, Lp)
     del u
+    wdt_job = dw["w_dt"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_dt"].expand(xdbl.shape[0], -1, -1)
+    delta, bc = CF.project_dt_bc(xdbl, wdt_job, L, N)
 
     # ---- fused scan --------------------------------------------------------------------------------------
     h0 = None if seq_ctx is None else seq_ctx.get("h0")
     want_state = seq_ctx is not None and seq_ctx.get("want_state", False)
-    yg, hlast, dtsum, _ = CF.scan_fwd(xz, xdbl, packed, jobs, L, halo=halo, h0=h0, want_state=want_state)
+    yg, hlast, dtsum, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, h0=h0, want_state=want_state)
     if want_state:
         seq_ctx["hlast"], seq_ctx["dtsum"] = hlast, dtsum
-        seq_ctx["xdbl"], seq_ctx["packed"], seq_ctx["jobs"] = xdbl, packed, jobs
+        seq_ctx["delta"], seq_ctx["bc"], seq_ctx["packed"], seq_ctx["jobs"] = delta, bc, packed, jobs
     del xz
 
     # ---- out_proj -------------------------------------------------------------------------------------------

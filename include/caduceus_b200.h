@@ -103,31 +103,33 @@ typedef struct {
 int cad_add_norm_bwd(const cad_add_norm_bwd_args* a, void* stream);
 int cad_add_norm_bwd_blocks(int64_t rows);   /* nblocks the backward wants for `rows` */
 
-/* ---- BiMamba inner path: (anti)causal depthwise conv + SiLU, dt/B/C, selective scan, gate.
+/* ---- BiMamba inner path: (anti)causal depthwise conv + SiLU, softplus(dt), selective scan, gate.
  *      Replaces causal_conv1d_fwd + selective_scan_cuda.fwd (and the two flips + second Mamba of
  *      ref:caduceus/modeling_caduceus.py:128-137; the RC strand of ref:caduceus/modeling_rcps.py:85-99).
  *
  *  A "job" j = (sequence s, direction p): one Mamba run over one sequence in one physical direction.
  *      xz      (nseq, 2E, ldxz)     in-proj output, channel-major; rows [0,E) = x, [E,2E) = z
- *      xdbl    (njobs, R+2N, ldxd)  x_proj output of job j: rows [0,R) dt low-rank, [R,R+N) B, [R+N,R+2N) C
+ *      delta   (njobs, E, ldd)      dt_raw = W_dt . x_dbl[0:R]  (the dt_proj GEMM; bias NOT added), io dtype
+ *      bc      (njobs, 2N, ldbc)    fp32 rows [0,N) = B, [N,2N) = C of job j (x_dbl[R:]); columns [L, ldbc)
+ *                                   must hold finite values (zeros).  Read through ONE TMA tensor map.
  *      out     (njobs, E, ldo)      gated scan output  y * silu(z)   (pre out_proj)
  *  job j uses sequence  seq_of_job[j], parameter set  pset_of_job[j]  (0 = mamba_fwd, 1 = mamba_rev) and runs
  *  right-to-left in physical time iff  rev_of_job[j].  Parameter sets are packed fp32:
- *      conv_w (P, E, 4) taps zero-padded at the front to 4;  conv_b (P, E);  dt_w (P, E, R);  dt_b (P, E);
+ *      conv_w (P, E, 4) taps zero-padded at the front to 4;  conv_b (P, E);  dt_b (P, E);
  *      A2 (P, E, N) = -exp(A_log) * log2(e);  Dskip (P, E).
  *  Semantics in LOGICAL time tau (tau = t, or L-1-t when reversed), SURVEY.md A.1/A.2/A.5:
  *      u[tau]  = silu(conv_b + sum_k conv_w[k] * x[tau-3+k])
- *      dt[tau] = softplus(dt_b + dt_w . xdbl[0:R, tau])      (threshold 20)
+ *      dt[tau] = softplus(delta[tau] + dt_b)                  (threshold 20)
  *      h[tau]  = exp2(dt*A2) * h[tau-1] + dt*B[tau]*u[tau],  h[-1] = h0 (or 0)
  *      y[tau]  = C[tau] . h[tau] + Dskip*u[tau];    out = y * silu(z)
  *  Optional sequence-sharding hooks: conv halo in, carry-state in, and per-job outputs
  *  (sum of dt per channel, final state) so that a shard can be composed with its neighbours.               */
 typedef struct {
   const void*  xz;
-  const void*  xdbl;
+  const void*  delta;
+  const float* bc;
   void*        out;
-  const float* conv_w; const float* conv_b; const float* dt_w; const float* dt_b;
-  const float* A2;     const float* Dskip;
+  const float* conv_w; const float* conv_b; const float* dt_b; const float* A2; const float* Dskip;
   const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;   /* device, (njobs) */
   /* sharding hooks, all optional (NULL): */
   const void*  halo;        /* (njobs, E, 3) x values preceding logical time 0, dtype io */
@@ -136,10 +138,10 @@ typedef struct {
   float*       dtsum;       /* (njobs, E) sum over tau of dt */
   /* optional saved tensors for backward (NULL in inference): */
   float*       chunk_state; /* (njobs, E, nchunks, N) state at the END of each 512-token logical chunk */
-  int64_t L, E, N, R, K;
-  int64_t ldxz, ldxd, ldo;
+  int64_t L, E, N, K;
+  int64_t ldxz, ldd, ldbc, ldo;
   int32_t nseq, njobs, npset;
-  int32_t io_dtype;         /* dtype of xz / xdbl / out / halo */
+  int32_t io_dtype;         /* dtype of xz / delta / out / halo */
   int32_t channels_per_cta; /* 0 = library picks so that the grid is ~ a multiple of the SM count */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
