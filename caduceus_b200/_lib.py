@@ -54,6 +54,26 @@ class ScanFwdArgs(C.Structure):
                 ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32)]
 
 
+class ScanBwdArgs(C.Structure):
+    _fields_ = [("xz", _p), ("delta", _p), ("bc", _p), ("dout", _p),
+                ("conv_w", _p), ("conv_b", _p), ("dt_b", _p), ("A2", _p), ("Dskip", _p),
+                ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p),
+                ("halo", _p), ("h0", _p), ("chunk_state", _p),
+                ("dz", _p), ("du", _p), ("ddelta", _p), ("dbc", _p),
+                ("ddt_b", _p), ("dA2", _p), ("dDskip", _p), ("dh0", _p),
+                ("L", _i64), ("E", _i64), ("N", _i64), ("K", _i64),
+                ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64), ("lddz", _i64), ("lddu", _i64),
+                ("lddd", _i64),
+                ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32)]
+
+
+class ConvBwdArgs(C.Structure):
+    _fields_ = [("xz", _p), ("du", _p), ("dx", _p), ("conv_w", _p), ("conv_b", _p), ("dconv_w", _p), ("dconv_b", _p),
+                ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
+                ("L", _i64), ("E", _i64), ("ldxz", _i64), ("lddu", _i64), ("lddx", _i64),
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32)]
+
+
 class ConvFwdArgs(C.Structure):
     _fields_ = [("xz", _p), ("u", _p), ("conv_w", _p), ("conv_b", _p),
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
@@ -74,6 +94,8 @@ SYMBOLS = {
     "cad_bimamba_scan_fwd": (C.c_int, [C.POINTER(ScanFwdArgs), _p]),
     "cad_scan_chunk_len": (C.c_int, []),
     "cad_conv_silu_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), _p]),
+    "cad_bimamba_scan_bwd": (C.c_int, [C.POINTER(ScanBwdArgs), _p]),
+    "cad_conv_silu_bwd": (C.c_int, [C.POINTER(ConvBwdArgs), _p]),
     "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),
 }
 

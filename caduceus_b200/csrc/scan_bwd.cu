@@ -443,18 +443,17 @@ __global__ void __launch_bounds__(256) conv_silu_bwd_kernel(cad_conv_bwd_args a)
       const int64_t t = rev ? t0 - 3 + j : t0 + j;
       float v = 0.f;
       if (t >= 0 && t < L) {
-        // conv pre-activation at physical t: fwd taps x[t-3..t]; rev taps x[t..t+3] reversed
-        const int o = (int)(t - (t0 - 3));             // index of x[t] in xw
+        // conv pre-activation at physical t: fwd taps x[t-3..t] (x[t] = xw[j+3]); rev taps x[t..t+3] (x[t] = xw[j])
         float c;
-        if (!rev) c = bias + w0 * xw[o - 3] + w1 * xw[o - 2] + w2 * xw[o - 1] + w3 * xw[o];
-        else      c = bias + w3 * xw[o] + w2 * xw[o + 1] + w1 * xw[o + 2] + w0 * xw[o + 3];
+        if (!rev) c = bias + w0 * xw[j] + w1 * xw[j + 1] + w2 * xw[j + 2] + w3 * xw[j + 3];
+        else      c = bias + w3 * xw[j] + w2 * xw[j + 1] + w1 * xw[j + 2] + w0 * xw[j + 3];
         const float sg = rcp(1.0f + ex2(-kLog2e * c));
         v = io<T>::to_f(du[t]) * sg * (1.0f + c * (1.0f - sg));
         // parameter gradients are owned by the thread whose OUTPUT range holds t
         if (t >= t0 && t < t0 + V) {
           s_b += v;
-          if (!rev) { s_w[0] += v * xw[o - 3]; s_w[1] += v * xw[o - 2]; s_w[2] += v * xw[o - 1]; s_w[3] += v * xw[o]; }
-          else      { s_w[3] += v * xw[o]; s_w[2] += v * xw[o + 1]; s_w[1] += v * xw[o + 2]; s_w[0] += v * xw[o + 3]; }
+          if (!rev) { s_w[0] += v * xw[j]; s_w[1] += v * xw[j + 1]; s_w[2] += v * xw[j + 2]; s_w[3] += v * xw[j + 3]; }
+          else      { s_w[3] += v * xw[j]; s_w[2] += v * xw[j + 1]; s_w[1] += v * xw[j + 2]; s_w[0] += v * xw[j + 3]; }
         }
       }
       dc[j] = v;

@@ -286,6 +286,112 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     return out, hlast, dtsum, cstate
 
 
+def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None, want_dh0=False,
+             channels_per_cta=0):
+    """Backward of scan_fwd: returns dz, du (scan path), ddelta (io dtype), dbc (fp32), ddt_b, dA2, dD, dh0."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    conv_w4, conv_b, dt_b, A2, Dk = packed
+    nseq, twoE, ldxz = xz.shape
+    E = twoE // 2
+    njobs, twoN, ldbc = bc.shape
+    P, _, N = A2.shape
+    dev = xz.device
+    dout = dout if dout.stride(-1) == 1 and dout.stride(1) % 16 == 0 else dout.contiguous()
+    dz = torch.empty(njobs, E, ldxz, device=dev, dtype=xz.dtype)
+    du = torch.empty(njobs, E, ldxz, device=dev, dtype=xz.dtype)
+    ddelta = torch.empty(njobs, E, ldxz, device=dev, dtype=xz.dtype)
+    dbc = torch.zeros(njobs, twoN, ldbc, device=dev, dtype=torch.float32)
+    ddt_b = torch.zeros(P, E, device=dev, dtype=torch.float32)
+    dA2 = torch.zeros(P, E, N, device=dev, dtype=torch.float32)
+    dD = torch.zeros(P, E, device=dev, dtype=torch.float32)
+    dh0 = torch.empty(njobs, E, N, device=dev, dtype=torch.float32) if want_dh0 else None
+    a = _lib.ScanBwdArgs(
+        _ptr(xz), _ptr(delta), _ptr(bc), _ptr(dout), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
+        _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(cstate),
+        _ptr(dz), _ptr(du), _ptr(ddelta), _ptr(dbc), _ptr(ddt_b), _ptr(dA2), _ptr(dD), _ptr(dh0),
+        L, E, N, 4, ldxz, delta.stride(1), ldbc, dout.stride(1), ldxz, ldxz, ldxz,
+        nseq, njobs, P, _dt(xz), channels_per_cta)
+    _lib.check(lib.cad_bimamba_scan_bwd(C.byref(a), _stream()), "cad_bimamba_scan_bwd")
+    _launched()
+    return dz, du, ddelta, dbc, ddt_b, dA2, dD, dh0
+
+
+def conv_silu_bwd(xz, du, conv_w4, conv_b, jobs, L, halo=None):
+    """Backward of conv_silu: dx (njobs, E, ld) in the io dtype, dconv_w (P, E, 4), dconv_b (P, E) fp32."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    nseq, twoE, ld = xz.shape
+    E = twoE // 2
+    njobs = seq.numel()
+    dx = torch.empty(njobs, E, ld, device=xz.device, dtype=xz.dtype)
+    dw = torch.zeros_like(conv_w4)
+    db = torch.zeros_like(conv_b)
+    a = _lib.ConvBwdArgs(_ptr(xz), _ptr(du), _ptr(dx), _ptr(conv_w4), _ptr(conv_b), _ptr(dw), _ptr(db),
+                         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), L, E, ld, du.stride(1), ld,
+                         nseq, njobs, _dt(xz))
+    _lib.check(lib.cad_conv_silu_bwd(C.byref(a), _stream()), "cad_conv_silu_bwd")
+    _launched()
+    return dx, dw, db
+
+
+class _BiMambaCoreFn(torch.autograd.Function):
+    """xz -> conv+SiLU -> x_proj -> (dt_proj, B, C) -> fused scan -> gated y, for all jobs of a BiMamba call.
+    Differentiable w.r.t. xz, the stacked x_proj / dt_proj weights and the packed scan parameters
+    (the backward of upstream's MambaInnerFn, SURVEY.md row A16, minus the in/out projections which stay in autograd)."""
+
+    @staticmethod
+    def forward(ctx, xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, jobs, L):
+        packed = (conv_w4, conv_b, dt_b, A2, Dk)
+        N = A2.shape[-1]
+        pset_l = jobs[1].long()
+        u = conv_silu(xz, conv_w4, conv_b, jobs, L)
+        xdbl = torch.bmm(w_x.index_select(0, pset_l), u)
+        del u
+        delta, bc = project_dt_bc(xdbl, w_dt.index_select(0, pset_l), L, N)
+        yg, _, _, cstate = scan_fwd(xz, delta, bc, packed, jobs, L, want_chunk_state=True)
+        ctx.save_for_backward(xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, delta, bc, cstate, xdbl)
+        ctx.jobs, ctx.L = jobs, L
+        return yg
+
+    @staticmethod
+    def backward(ctx, dyg):
+        xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, delta, bc, cstate, xdbl = ctx.saved_tensors
+        jobs, L = ctx.jobs, ctx.L
+        packed = (conv_w4, conv_b, dt_b, A2, Dk)
+        P, _, N = A2.shape
+        R = w_dt.shape[-1]
+        pset_l, seq_l = jobs[1].long(), jobs[0].long()
+        act = xz.dtype
+        dz, du, ddelta, dbc, ddt_b, dA2, dD, _ = scan_bwd(xz, delta, bc, dyg, packed, jobs, L, cstate)
+        ld = xz.shape[-1]
+        # dt_proj and x_proj backward (cuBLAS): d x_dbl = [W_dt^T d dt_raw ; dB ; dC]
+        wdt_job = w_dt.index_select(0, pset_l)
+        wx_job = w_x.index_select(0, pset_l)
+        dxdbl = torch.zeros(xdbl.shape, device=xz.device, dtype=act)
+        dxdbl[:, :R, :L] = torch.bmm(wdt_job.transpose(1, 2), ddelta[..., :L])
+        dxdbl[:, R:, :L] = dbc[..., :L].to(act)
+        dw_dt = torch.zeros(w_dt.shape, device=xz.device, dtype=torch.float32)
+        dw_dt.index_add_(0, pset_l, torch.bmm(ddelta[..., :L], xdbl[:, :R, :L].transpose(1, 2)).float())
+        u = conv_silu(xz, conv_w4, conv_b, jobs, L)
+        dw_x = torch.zeros(w_x.shape, device=xz.device, dtype=torch.float32)
+        dw_x.index_add_(0, pset_l, torch.bmm(dxdbl[..., :L], u[..., :L].transpose(1, 2)).float())
+        del u
+        du_total = torch.baddbmm(du, wx_job.transpose(1, 2), dxdbl)
+        dx, dconv_w, dconv_b = conv_silu_bwd(xz, du_total, conv_w4, conv_b, jobs, L)
+        # several jobs (directions) may share one in-proj output: sum their gradients
+        dxz = torch.zeros(xz.shape, device=xz.device, dtype=torch.float32 if xz.dtype == torch.float32 else act)
+        E = dx.shape[1]
+        dxz[:, :E].index_add_(0, seq_l, dx)
+        dxz[:, E:].index_add_(0, seq_l, dz)
+        dxz[..., L:] = 0
+        return (dxz, dw_x.to(w_x.dtype), dw_dt.to(w_dt.dtype), dconv_w, dconv_b, ddt_b, dA2, dD, None, None)
+
+
+def bimamba_core(xz, w_x, w_dt, packed, jobs, L):
+    return _BiMambaCoreFn.apply(xz, w_x, w_dt, *packed, jobs, L)
+
+
 def microbench(which):
     lib = _lib.load()
     v = C.c_double(0.0)

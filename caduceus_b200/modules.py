@@ -198,11 +198,12 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
         hidden = hidden.contiguous()
     dev = hidden.device
     grad = torch.is_grad_enabled() and (hidden.requires_grad or any(p.requires_grad for m in dirs for p in m.parameters()))
-    if grad:
-        raise NotImplementedError("caduceus_b200: backward of the fused scan is not wired yet")
-
     tied_in = ndir == 1 or (dirs[1].in_proj.weight is dirs[0].in_proj.weight and dirs[1].in_proj.bias is dirs[0].in_proj.bias)
     tied_out = ndir == 1 or (dirs[1].out_proj.weight is dirs[0].out_proj.weight and dirs[1].out_proj.bias is dirs[0].out_proj.bias)
+    if grad:
+        if seq_ctx is not None:
+            raise NotImplementedError("caduceus_b200: sequence-sharded training is not wired yet")
+        return _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out)
     nw = 1 if tied_in else ndir
     jobs = CF.job_tables(B, nstrand, ndir, not tied_in, dev)
     Lp = CF.round_up(max(L, 1), 16)
@@ -294,3 +295,66 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
                 else:
                     raise NotImplementedError(f"`{strategy}` for bi-directionality not implemented!")
     return out
+
+
+def _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out):
+    """Differentiable variant of `bimamba_inner`: the dense projections are plain autograd matmuls, everything
+    between them (conv, x_proj, dt_proj, scan, gate) is ONE custom Function with hand-written backward kernels
+    (CF.bimamba_core).  Same algebra, same job layout as the inference path."""
+    ndir = len(dirs)
+    m0 = dirs[0]
+    B, L, width = hidden.shape
+    D = width // nstrand
+    E = m0.d_inner
+    nw = 1 if tied_in else ndir
+    dev = hidden.device
+    jobs = CF.job_tables(B, nstrand, ndir, not tied_in, dev)
+    Lp = CF.round_up(max(L, 1), 16)
+
+    seqs = []
+    for s in range(nstrand):
+        hT = hidden[:, :, s * D:(s + 1) * D].transpose(1, 2)                       # (B, D, L)
+        for w in range(nw):
+            w_in = dirs[w].in_proj.weight if s == 0 else dirs[w].in_proj.weight.flip(1)
+            v = torch.matmul(w_in.to(act), hT)                                     # (B, 2E, L)
+            if dirs[w].in_proj.bias is not None:
+                v = v + dirs[w].in_proj.bias.to(act)[None, :, None]
+            seqs.append(v)
+    xz = torch.stack(seqs, dim=1)                                                  # (B, S*W, 2E, L)
+    if Lp != L:
+        xz = F.pad(xz, (0, Lp - L))
+    xz = xz.reshape(B * nstrand * nw, 2 * E, Lp)
+
+    w_x = torch.stack([m.x_proj.weight.to(act) for m in dirs])
+    w_dt = torch.stack([m.dt_proj.weight.to(act) for m in dirs])
+    packed = pack_scan_params(dirs)
+    yg = CF.bimamba_core(xz, w_x, w_dt, packed, jobs, L)                           # (njobs, E, Lp)
+    yg = yg.view(B, nstrand, ndir, E, Lp)[..., :L]
+
+    outs = []
+    for s in range(nstrand):
+        w_out = [(m.out_proj.weight if s == 0 else m.out_proj.weight.flip(0)).to(act) for m in dirs]
+        b_out = [None if m.out_proj.bias is None else (m.out_proj.bias if s == 0 else m.out_proj.bias.flip(0)).to(act)
+                 for m in dirs]
+        if tied_out and (ndir == 1 or strategy == "add"):
+            a_t = yg[:, s].reshape(B, ndir * E, L).transpose(1, 2)                 # (B, L, ndir*E)
+            o = torch.matmul(a_t, torch.cat(w_out, dim=1).t())
+            if b_out[0] is not None:
+                o = o + b_out[0] * ndir
+        else:
+            parts = []
+            for d in range(ndir):
+                od = torch.matmul(yg[:, s, d].transpose(1, 2), w_out[d].t())
+                if b_out[d] is not None:
+                    od = od + b_out[d]
+                parts.append(od)
+            if ndir == 1:
+                o = parts[0]
+            elif strategy == "add":
+                o = parts[0] + parts[1]
+            elif strategy == "ew_multiply":
+                o = parts[0] * parts[1]
+            else:
+                raise NotImplementedError(f"`{strategy}` for bi-directionality not implemented!")
+        outs.append(o)
+    return outs[0] if nstrand == 1 else torch.cat(outs, dim=-1)

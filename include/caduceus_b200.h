@@ -147,6 +147,40 @@ typedef struct {
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
 
+/* ---- backward of cad_bimamba_scan_fwd (replaces selective_scan_cuda.bwd).
+ *      Inputs as the forward plus dout (njobs, E, ldo) and the forward's chunk_state.  Outputs:
+ *        dz      (njobs, E, lddz)   gradient of the gate input z                               io dtype
+ *        du      (njobs, E, lddu)   gradient w.r.t. u = silu(conv(x)) from the scan path       io dtype
+ *        ddelta  (njobs, E, lddd)   gradient w.r.t. dt_raw                                     io dtype
+ *        dbc     (njobs, 2N, ldbc)  gradient w.r.t. B/C rows, fp32, ACCUMULATED (caller zero-fills)
+ *        ddt_b, dDskip (P, E), dA2 (P, E, N)   fp32, ACCUMULATED (caller zero-fills)
+ *        dh0     (njobs, E, N)      gradient w.r.t. the carry-in state, or NULL                              */
+typedef struct {
+  const void*  xz; const void* delta; const float* bc; const void* dout;
+  const float* conv_w; const float* conv_b; const float* dt_b; const float* A2; const float* Dskip;
+  const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;
+  const void*  halo; const float* h0; const float* chunk_state;
+  void* dz; void* du; void* ddelta; float* dbc;
+  float* ddt_b; float* dA2; float* dDskip; float* dh0;
+  int64_t L, E, N, K;
+  int64_t ldxz, ldd, ldbc, ldo, lddz, lddu, lddd;
+  int32_t nseq, njobs, npset, io_dtype, channels_per_cta;
+} cad_scan_bwd_args;
+int cad_bimamba_scan_bwd(const cad_scan_bwd_args* a, void* stream);
+
+/* backward of the depthwise (anti)causal conv + SiLU: given du (total gradient of u), recomputes the conv
+ * pre-activation from x and writes dx (njobs, E, lddx); dconv_w (P, E, 4) / dconv_b (P, E) are ACCUMULATED.
+ * Replaces causal_conv1d_cuda.causal_conv1d_bwd.                                                              */
+typedef struct {
+  const void* xz; const void* du; void* dx;
+  const float* conv_w; const float* conv_b; float* dconv_w; float* dconv_b;
+  const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;
+  const void* halo;
+  int64_t L, E, ldxz, lddu, lddx;
+  int32_t nseq, njobs, io_dtype;
+} cad_conv_bwd_args;
+int cad_conv_silu_bwd(const cad_conv_bwd_args* a, void* stream);
+
 /* v1 helper: u = silu(conv(x)) materialised per job for the x_proj GEMM  (njobs, E, ldu). */
 typedef struct {
   const void* xz; void* u;
