@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--n-layer", type=int, default=16)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="none", choices=["none", "seq"],
+                    help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
     return ap.parse_args()
 
 
@@ -189,6 +191,20 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    shard_seq = a.shard == "seq" and world > 1
+    if shard_seq:       # every rank holds tokens [rank*L/P, (rank+1)*L/P) of the SAME sequences
+        from caduceus_b200 import seqshard
+        Ls = a.seqlen // world
+        host_ids = [make_ids(torch, a.batch, a.seqlen, 100 + i)[:, rank * Ls:(rank + 1) * Ls].contiguous().pin_memory()
+                    for i in range(nbuf)]
+        dev_ids = [h.to(dev) for h in host_ids]
+        host_out = torch.empty(a.batch, Ls, cfg.vocab_size, dtype=torch.float32).pin_memory()
+        _model = model
+
+        def model(ids):          # noqa: F811  (sequence-parallel wrapper around the same module)
+            with seqshard.sequence_parallel():
+                return _model(ids)
+
     def step_device(i):
         with torch.no_grad():
             return model(dev_ids[i % nbuf]).logits
@@ -233,7 +249,7 @@ def run_b200(a):
         sampler.stop_flag.set()
         sampler.join()
 
-    nt_per_step = a.batch * a.seqlen * world
+    nt_per_step = a.batch * a.seqlen * (1 if shard_seq else world)
     value = nt_per_step * a.steps / (ms_dev * 1e-3)
     e2e_value = nt_per_step * a.steps / (ms_e2e * 1e-3)
 
@@ -276,9 +292,11 @@ def run_b200(a):
                    "token_directions_per_s": rate}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
+            "scaling": "strong" if shard_seq else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(a), "parallelism": f"dp{world} (independent sequences per GPU)",
+            "config": {"workload": workload_name(a), "parallelism": (f"sp{world} (one sequence sharded on the sequence axis, 2 tiny all_gathers per layer)"
+                                       if shard_seq else f"dp{world} (independent sequences per GPU)"),
                        "l2": "per-step working set > 1 GB >> 126 MB L2; 4 rotating input batches"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": a.batch * a.seqlen * 8 * world,

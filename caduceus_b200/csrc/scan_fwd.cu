@@ -34,7 +34,7 @@ struct ScanSmem {
 };
 
 // One chunk of one channel.  TAIL: the chunk straddles the sequence end (per-token masks, halo in the pad).
-template <typename T, int N, bool REV, bool TAIL>
+template <typename T, int N, bool REV, bool TAIL, bool STATE_ONLY>
 __device__ __forceinline__ void scan_chunk(
     const cad_scan_fwd_args& a, const ScanSmem& sm, int lane, int seg, const uint32_t (&poff)[4],
     const T* __restrict__ xrow, const T* __restrict__ zrow, const T* __restrict__ drow, T* __restrict__ orow,
@@ -126,7 +126,7 @@ __device__ __forceinline__ void scan_chunk(
     float h = __shfl_up_sync(0xffffffffu, hl, 1);
     if (lane == 0) h = cin;
     if (lane == 31) my_carry[n] = hl;          // state at the end of this chunk
-    {
+    if (!STATE_ONLY) {
       const unsigned char* rowp = tile_b + (N + n) * (kChunk * 4);
       float cv[kTok];
 #pragma unroll
@@ -150,7 +150,7 @@ __device__ __forceinline__ void scan_chunk(
   }
 
   // ---- 5. gate with silu(z) and store (physical order) ---------------------------------------------------
-  if (seg_in && active) {
+  if (!STATE_ONLY && seg_in && active) {
     float zs[kTok], o[kTok];
     load_vec<T, kTok>(zrow + tseg, zs);
 #pragma unroll
@@ -166,7 +166,7 @@ __device__ __forceinline__ void scan_chunk(
   (void)EPV;
 }
 
-template <typename T, int N, bool REV>
+template <typename T, int N, bool REV, bool STATE_ONLY>
 __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUtensorMap* tmap, int job, int seq,
                                          int pset, const ScanSmem& sm) {
   const int lane = threadIdx.x & 31;
@@ -234,10 +234,10 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     const int next_c1 = (int)((REV ? pcidx - 1 : pcidx + 1) * blocks_per_chunk);
     const bool tail = (pcidx + 1) * kChunk > L;
     if (tail)
-      scan_chunk<T, N, REV, true>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, REV, true, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                   prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row);
     else
-      scan_chunk<T, N, REV, false>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, REV, false, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                    prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row);
     parity ^= 1;
     if (a.chunk_state) {
@@ -257,7 +257,7 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
   }
 }
 
-template <typename T, int N>
+template <typename T, int N, bool STATE_ONLY>
 __global__ void __launch_bounds__(kMaxG * 32, 2)
 bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_raw[];
@@ -271,8 +271,8 @@ bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUten
   if (threadIdx.x == 0) mbar_init(sm.bar, 1);
   const int job = blockIdx.y;
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
-  if (rev) scan_job<T, N, true>(a, &tmap, job, seq, pset, sm);
-  else     scan_job<T, N, false>(a, &tmap, job, seq, pset, sm);
+  if (rev) scan_job<T, N, true, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
+  else     scan_job<T, N, false, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
 }
 
 template <typename T, int N>
@@ -281,7 +281,7 @@ static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
   if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * N, a.ldbc, a.L, 2 * N) != 0) return -1;
 
   const size_t smem = 1024 + (size_t)2 * N * kChunk * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16;
-  auto kern = bimamba_scan_fwd_kernel<T, N>;
+  auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, true> : bimamba_scan_fwd_kernel<T, N, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
@@ -299,7 +299,7 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   CAD_REQUIRE(a, "cad_bimamba_scan_fwd: null argument block");
   CAD_REQUIRE(a->L >= 0 && a->E > 0 && a->njobs > 0 && a->nseq > 0, "cad_bimamba_scan_fwd: bad sizes");
   if (a->L == 0) return 0;
-  CAD_REQUIRE(a->xz && a->delta && a->bc && a->out && a->conv_w && a->conv_b && a->dt_b && a->A2 && a->Dskip &&
+  CAD_REQUIRE(a->xz && a->delta && a->bc && (a->out || a->state_only) && a->conv_w && a->conv_b && a->dt_b && a->A2 && a->Dskip &&
               a->seq_of_job && a->pset_of_job && a->rev_of_job, "cad_bimamba_scan_fwd: null pointer");
   CAD_REQUIRE(a->N == 16, "cad_bimamba_scan_fwd: d_state = %lld not built (only 16)", (long long)a->N);
   CAD_REQUIRE(a->K >= 1 && a->K <= 4, "cad_bimamba_scan_fwd: d_conv = %lld out of range [1, 4]", (long long)a->K);
@@ -308,6 +308,7 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   CAD_REQUIRE(a->ldbc % 32 == 0 && a->ldbc >= a->L, "cad_bimamba_scan_fwd: ldbc must be a multiple of 32 and >= L");
   CAD_REQUIRE(aligned16(a->xz) && aligned16(a->delta) && aligned16(a->bc) && aligned16(a->out),
               "cad_bimamba_scan_fwd: xz/delta/bc/out must be 16-byte aligned");
+  CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int G = a->channels_per_cta;
   if (G <= 0) {

@@ -252,7 +252,7 @@ def project_dt_bc(xdbl, dt_w_job, L, N):
 
 
 def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
-             channels_per_cta=0):
+             channels_per_cta=0, state_only=False):
     """Launch the fused bidirectional scan.
     xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld)."""
     lib = _lib.load()
@@ -263,7 +263,8 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     njobs, twoN, ldbc = bc.shape
     P, _, N = A2.shape
     assert twoN == 2 * N and delta.shape[0] == njobs and delta.shape[1] == E
-    out = torch.empty(njobs, E, ldxz, device=xz.device, dtype=xz.dtype)
+    want_state = want_state or state_only
+    out = None if state_only else torch.empty(njobs, E, ldxz, device=xz.device, dtype=xz.dtype)
     hlast = torch.empty(njobs, E, N, device=xz.device, dtype=torch.float32) if want_state else None
     dtsum = torch.empty(njobs, E, device=xz.device, dtype=torch.float32) if want_state else None
     chunk = lib.cad_scan_chunk_len()
@@ -273,7 +274,7 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     a = _lib.ScanFwdArgs(
         _ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
-        L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta)
+        L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only))
     ev = None
     if SCAN_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

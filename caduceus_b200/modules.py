@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import functional as CF
+from . import seqshard
 
 _LOG2E = 1.4426950408889634
 
@@ -172,7 +173,7 @@ def _act_dtype(hidden):
     return hidden.dtype
 
 
-def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_ctx=None):
+def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
     """BiMambaWrapper.forward (ref:caduceus/modeling_caduceus.py:122-140) — and, with nstrand=2, the whole
     RCPSWrapper(BiMambaWrapper) of ref:caduceus/modeling_rcps.py:85-99 — as one fused pipeline:
 
@@ -200,9 +201,10 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
     grad = torch.is_grad_enabled() and (hidden.requires_grad or any(p.requires_grad for m in dirs for p in m.parameters()))
     tied_in = ndir == 1 or (dirs[1].in_proj.weight is dirs[0].in_proj.weight and dirs[1].in_proj.bias is dirs[0].in_proj.bias)
     tied_out = ndir == 1 or (dirs[1].out_proj.weight is dirs[0].out_proj.weight and dirs[1].out_proj.bias is dirs[0].out_proj.bias)
+    shard = seqshard.current()
     if grad:
-        if seq_ctx is not None:
-            raise NotImplementedError("caduceus_b200: sequence-sharded training is not wired yet")
+        if shard is not None and shard.world > 1:
+            raise NotImplementedError("caduceus_b200: sequence-sharded TRAINING is not wired yet (forward only)")
         return _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out)
     nw = 1 if tied_in else ndir
     jobs = CF.job_tables(B, nstrand, ndir, not tied_in, dev)
@@ -250,7 +252,10 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
     xz = xz.view(B * nstrand * nw, 2 * E, Lp)
 
     # ---- conv + SiLU, x_proj GEMM ----------------------------------------------------------------------
-    halo = None if seq_ctx is None else seq_ctx.get("halo")
+    sharded = shard is not None and shard.world > 1
+    halo = None
+    if sharded:      # the 3 conv samples that logically precede this shard (one tiny all_gather)
+        halo = seqshard.gather_halo(xz[:, :E, :], L, jobs[0], jobs[2], shard).to(act)
     u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                        # (njobs, E, Lp)
     wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
     xdbl = torch.bmm(wx_job, u)                                                           # (njobs, R+2N, Lp)
@@ -259,12 +264,11 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1, seq_c
     delta, bc = CF.project_dt_bc(xdbl, wdt_job, L, N)
 
     # ---- fused scan --------------------------------------------------------------------------------------
-    h0 = None if seq_ctx is None else seq_ctx.get("h0")
-    want_state = seq_ctx is not None and seq_ctx.get("want_state", False)
-    yg, hlast, dtsum, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, h0=h0, want_state=want_state)
-    if want_state:
-        seq_ctx["hlast"], seq_ctx["dtsum"] = hlast, dtsum
-        seq_ctx["delta"], seq_ctx["bc"], seq_ctx["packed"], seq_ctx["jobs"] = delta, bc, packed, jobs
+    h0 = None
+    if sharded:      # zero-carry pass -> all_gather(H, sum dt) -> compose this shard's carry-in (seqshard.py)
+        _, hl, ds, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, state_only=True)
+        h0 = seqshard.gather_carry(hl, ds, packed[3], jobs[1], jobs[2], shard)
+    yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, h0=h0)
     del xz
 
     # ---- out_proj -------------------------------------------------------------------------------------------
