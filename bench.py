@@ -44,14 +44,17 @@ def parse():
     ap.add_argument("--n-layer", type=int, default=16)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="train: MLM step = forward + loss + backward + AdamW under bf16 autocast (BASELINE configs[3] on 1 GPU)")
     ap.add_argument("--shard", default="none", choices=["none", "seq"],
                     help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
     return ap.parse_args()
 
 
 def workload_name(a):
+    what = "forward" if a.mode == "forward" else "MLM train step (fwd+bwd+AdamW, autocast)"
     return (f"Caduceus-{'PS (rcps=true)' if a.model == 'ps' else 'Ph'} d_model={a.d_model} n_layer={a.n_layer} "
-            f"seq_len={a.seqlen} bf16 forward, batch {a.batch}/GPU")
+            f"seq_len={a.seqlen} bf16 {what}, batch {a.batch}/GPU")
 
 
 def scans_per_nt(a):
@@ -177,7 +180,13 @@ def run_b200(a):
         initializer_cfg=dict(initializer_range=0.02, rescale_prenorm_residual=True, n_residuals_per_layer=1),
         bidirectional=True, bidirectional_strategy="add", bidirectional_weight_tie=True, rcps=(a.model == "ps"),
         complement_map=dict(CMAP) if a.model == "ps" else None)
-    model = caduceus.CaduceusForMaskedLM(cfg).to(dev).to(torch.bfloat16).eval()
+    train = a.mode == "train"
+    if train:
+        cfg.pad_token_id = 4
+        model = caduceus.CaduceusForMaskedLM(cfg).to(dev).train()          # fp32 master weights, bf16 autocast
+        opt = torch.optim.AdamW(model.parameters(), lr=8e-3, weight_decay=0.1, fused=True)
+    else:
+        model = caduceus.CaduceusForMaskedLM(cfg).to(dev).to(torch.bfloat16).eval()
 
     # a ring of distinct input batches in pinned host memory; each step's activations (> 1 GB of xz / scan
     # buffers at L=131072) exceed the 126 MB L2, so no explicit flush is needed between iterations
@@ -205,13 +214,41 @@ def run_b200(a):
             with seqshard.sequence_parallel():
                 return _model(ids)
 
+    def mlm(ids):        # 15 % positions: 80 % [MASK], 10 % random, 10 % kept; target PAD elsewhere
+        g = torch.Generator(device=ids.device).manual_seed(1)
+        r = torch.rand(ids.shape, device=ids.device, generator=g)
+        sel = r < 0.15
+        inp = ids.clone()
+        inp[sel & (r < 0.12)] = 3
+        rnd = sel & (r >= 0.12) & (r < 0.135)
+        inp[rnd] = torch.randint(0, 12, (int(rnd.sum()),), device=ids.device, generator=g)
+        tgt = torch.where(sel, ids, torch.full_like(ids, 4))
+        return inp, tgt
+
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def train_step(ids):
+        inp, tgt = mlm(ids)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = model(inp, labels=tgt).loss
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
     def step_device(i):
+        if train:
+            return train_step(dev_ids[i % nbuf])
         with torch.no_grad():
             return model(dev_ids[i % nbuf]).logits
 
     def step_e2e(i):
+        ids = host_ids[i % nbuf].to(dev, non_blocking=True)
+        if train:
+            loss = train_step(ids)
+            host_loss.copy_(loss.detach(), non_blocking=True)
+            return loss
         with torch.no_grad():
-            ids = host_ids[i % nbuf].to(dev, non_blocking=True)
             logits = model(ids).logits
             host_out.copy_(logits, non_blocking=True)
         return logits
@@ -294,13 +331,13 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
             "scaling": "strong" if shard_seq else "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16", "data": "synthetic", "mode": a.mode,
             "config": {"workload": workload_name(a), "parallelism": (f"sp{world} (one sequence sharded on the sequence axis, 2 tiny all_gathers per layer)"
                                        if shard_seq else f"dp{world} (independent sequences per GPU)"),
                        "l2": "per-step working set > 1 GB >> 126 MB L2; 4 rotating input batches"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": a.batch * a.seqlen * 8 * world,
-                    "d2h_bytes_per_step": a.batch * a.seqlen * cfg.vocab_size * 4 * world},
+                    "d2h_bytes_per_step": (4 if train else a.batch * a.seqlen * cfg.vocab_size * 4) * world},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -124,6 +124,23 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 // silu(v) = v / (1 + exp(-v))
 __device__ __forceinline__ float silu(float v) { return v * rcp(1.0f + ex2(-kLog2e * v)); }
+// silu for 16-bit I/O: x*sigmoid(x) = h + h*tanh(h), h = x/2 — ONE MUFU (tanh.approx, rel. error 2^-11, below the
+// bf16/fp16 rounding of the result) instead of two (ex2 + rcp).  The scan is MUFU-bound, so the activations of its
+// prologue/epilogue are worth 2 of the ~22 MUFU ops per (token, channel).  fp32 I/O keeps the exact form.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T>
+__device__ __forceinline__ float silu_io(float v) {
+  if constexpr (sizeof(T) == 2) {
+    const float h = 0.5f * v;
+    return fmaf(h, tanh_approx(h), h);
+  } else {
+    return silu(v);
+  }
+}
 // softplus with torch's threshold (20): log1p(exp(v)) = ln2 * log2(1 + 2^(v*log2e))
 __device__ __forceinline__ float softplus(float v) {
   const float w = ex2(kLog2e * v);                       // e^v

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) conv_silu_fwd_kernel(cad_conv_fwd_args a)
     float acc;
     if (!rev) acc = bias + w0 * win[i] + w1 * win[i + 1] + w2 * win[i + 2] + w3 * win[i + 3];
     else      acc = bias + w3 * win[i] + w2 * win[i + 1] + w1 * win[i + 2] + w0 * win[i + 3];
-    o[i] = io<T>::from_f(silu(acc));
+    o[i] = io<T>::from_f(silu_io<T>(acc));
   }
   // the vector may run past L inside the (16-element padded) row pitch: harmless, the pad is never consumed
   *reinterpret_cast<uint4*>(u + t0) = outv;

@@ -51,14 +51,16 @@ template <typename T>
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(
     const int64_t* __restrict__ ids, const int64_t* __restrict__ cmap, const T* __restrict__ dout,
     float* __restrict__ dW, int64_t rows, int64_t V, int64_t D, int rcps, int64_t rows_per_block) {
-  extern __shared__ float acc[];   // V * D
-  for (int64_t i = threadIdx.x; i < V * D; i += blockDim.x) acc[i] = 0.f;
+  extern __shared__ float acc[];   // 2 tiles of V * D: [0] forward half, [1] RC half
+  float* acc_rc = acc + V * D;
+  for (int64_t i = threadIdx.x; i < 2 * V * D; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   const int64_t width = rcps ? 2 * D : D;
-  // thread t owns channel set {t, t+blockDim, ...}; rows are walked sequentially -> no smem conflicts
-  // between threads (distinct channels), no atomics needed inside the block.
+  // thread t owns channel set {t, t+blockDim, ...} of EACH tile; rows are walked sequentially, so inside a tile no
+  // two threads ever touch the same address.  The RC half lands on reversed columns (owned by other threads), hence
+  // its own tile: with a self-complementary token (cmap[id] == id: PAD, MASK, N) both halves hit the same row.
   for (int64_t r = r0; r < r1; ++r) {
     int64_t id = ids[r];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
@@ -66,12 +68,12 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(
     for (int64_t c = threadIdx.x; c < D; c += blockDim.x) acc[id * D + c] += io<T>::to_f(g[c]);
     if (rcps) {
       const int64_t idc = cmap[id];
-      for (int64_t c = threadIdx.x; c < D; c += blockDim.x) acc[idc * D + (D - 1 - c)] += io<T>::to_f(g[D + c]);
+      for (int64_t c = threadIdx.x; c < D; c += blockDim.x) acc_rc[idc * D + (D - 1 - c)] += io<T>::to_f(g[D + c]);
     }
   }
   __syncthreads();
   for (int64_t i = threadIdx.x; i < V * D; i += blockDim.x) {
-    float v = acc[i];
+    const float v = acc[i] + acc_rc[i];
     if (v != 0.f) atomicAdd(dW + i, v);
   }
 }
@@ -109,7 +111,7 @@ extern "C" int cad_embedding_bwd(const cad_embedding_bwd_args* a, void* stream_)
   if (a->B * a->L == 0) return 0;
   CAD_REQUIRE(a->ids && a->dout && a->dweight, "cad_embedding_bwd: null pointer");
   CAD_REQUIRE(!a->rcps || a->cmap, "cad_embedding_bwd: rcps needs a complement map");
-  CAD_REQUIRE(a->V * a->D * 4 <= 48 * 1024, "cad_embedding_bwd: V*D too large for the smem tile");
+  CAD_REQUIRE(2 * a->V * a->D * 4 <= 48 * 1024, "cad_embedding_bwd: V*D too large for the smem tiles");
   const int64_t rows = a->B * a->L;
   if (rows == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -117,7 +119,7 @@ extern "C" int cad_embedding_bwd(const cad_embedding_bwd_args* a, void* stream_)
   const int64_t rpb = (rows + blocks - 1) / blocks;
   const int64_t nblk = (rows + rpb - 1) / rpb;
   CAD_DISPATCH_DTYPE(a->dtype, T,
-    embedding_bwd_kernel<T><<<(unsigned)nblk, 256, (size_t)(a->V * a->D * 4), stream>>>(
+    embedding_bwd_kernel<T><<<(unsigned)nblk, 256, (size_t)(2 * a->V * a->D * 4), stream>>>(
         a->ids, a->cmap, static_cast<const T*>(a->dout), a->dweight, rows, a->V, a->D, a->rcps, rpb));
   CAD_LAUNCH_CHECK();
   return 0;

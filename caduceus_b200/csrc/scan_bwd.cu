@@ -156,7 +156,7 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
       xl[2] = lane == 0 ? p2 : u2;
 #pragma unroll
       for (int i = 0; i < kTok; ++i) {
-        u[i] = silu(cb + cw[0] * xl[i] + cw[1] * xl[i + 1] + cw[2] * xl[i + 2] + cw[3] * xl[i + 3]);
+        u[i] = silu_io<T>(cb + cw[0] * xl[i] + cw[1] * xl[i + 1] + cw[2] * xl[i + 2] + cw[3] * xl[i + 3]);
         const float raw = dr[phys(i)] + dtb;
         float d = softplus(raw);
         float sg = raw > 20.0f ? 1.0f : sigmoidf_fast(raw);
@@ -166,7 +166,7 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
         sgd[i] = sg;
         dsum += d;
         const float zz = zs[phys(i)];
-        dy[i] = masked ? 0.f : gs[phys(i)] * silu(zz);
+        dy[i] = masked ? 0.f : gs[phys(i)] * silu_io<T>(zz);
       }
     }
     float ddt[kTok], dug[kTok], y[kTok];

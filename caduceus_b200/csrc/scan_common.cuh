@@ -41,6 +41,30 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
 }
 
 
+// explicit shared-space accesses with 32-bit addresses (generic LD/ST through 64-bit pointers cost address
+// arithmetic and the slower generic path: profiles/r1_v2_scan_ncu_summary.txt shows 0.63 generic LD per element)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// one step of the inclusive (decay, state) warp scan: lanes >= OFF absorb the aggregate of lane - OFF
+template <int OFF>
+__device__ __forceinline__ void scan_step_up(float& P, float& H, int lane) {
+  const float Pp = __shfl_up_sync(0xffffffffu, P, OFF);
+  const float Hp = __shfl_up_sync(0xffffffffu, H, OFF);
+  asm("{\n.reg .pred q;\nsetp.ge.s32 q, %4, %5;\n@q fma.rn.f32 %0, %1, %2, %0;\n@q mul.f32 %1, %1, %3;\n}"
+      : "+f"(H), "+f"(P) : "f"(Hp), "f"(Pp), "r"(lane), "n"(OFF));
+}
+
 // this lane's four 16-byte pieces inside a TMA-swizzled tile row (see scan_fwd.cu): SWIZZLE_128B stores 16-byte
 // chunk c of 128-byte line l at chunk position c ^ (l & 7); a tile row is 16 consecutive lines.
 __device__ __forceinline__ void tile_piece_offsets(int seg, uint32_t (&poff)[4]) {

@@ -80,7 +80,7 @@ __device__ __forceinline__ void scan_chunk(
     for (int k = 0; k < 3; ++k) prev3[k] = __shfl_sync(0xffffffffu, xl[kTok + k], 31);
 #pragma unroll
     for (int i = 0; i < kTok; ++i) {
-      const float u = silu(cb + cw[0] * xl[i] + cw[1] * xl[i + 1] + cw[2] * xl[i + 2] + cw[3] * xl[i + 3]);
+      const float u = silu_io<T>(cb + cw[0] * xl[i] + cw[1] * xl[i + 1] + cw[2] * xl[i + 2] + cw[3] * xl[i + 3]);
       float d = softplus(dr[phys(i)] + dtb);
       if (TAIL && tseg + phys(i) >= L) d = 0.f;     // masked token: a = 1, b = 0 -> state passes through
       dt[i] = d;
@@ -93,18 +93,19 @@ __device__ __forceinline__ void scan_chunk(
 
   // ---- 3. the scan, one state at a time, on the TMA-staged B/C tile ------------------------------------
   mbar_wait(sm.bar, parity);
-  const unsigned char* tile_b = reinterpret_cast<const unsigned char*>(sm.tile);
+  const uint32_t tile_s = smem_u32(sm.tile);
+  const uint32_t a2_s = smem_u32(my_a2), carry_s = smem_u32(my_carry);
 #pragma unroll 1
   for (int n = 0; n < N; ++n) {
-    const float A2n = my_a2[n];
-    const float cin = my_carry[n];
+    const float A2n = lds32(a2_s + 4 * n);
+    const float cin = lds32(carry_s + 4 * n);
     float av[kTok], bv[kTok];
     float hl = (lane == 0) ? cin : 0.f;
     {
-      const unsigned char* rowp = tile_b + n * (kChunk * 4);
+      const uint32_t rowp = tile_s + n * (kChunk * 4);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 q = *reinterpret_cast<const float4*>(rowp + poff[k]);
+        const float4 q = lds128(rowp + poff[k]);
         const float bq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -117,27 +118,31 @@ __device__ __forceinline__ void scan_chunk(
       for (int i = 0; i < kTok; ++i) hl = fmaf(av[i], hl, bv[i]);
     }
     float P = ex2(A2n * dsum);
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const float Pp = __shfl_up_sync(0xffffffffu, P, off);
-      const float Hp = __shfl_up_sync(0xffffffffu, hl, off);
-      if (lane >= off) { hl = fmaf(P, Hp, hl); P *= Pp; }
-    }
+    scan_step_up<1>(P, hl, lane);
+    scan_step_up<2>(P, hl, lane);
+    scan_step_up<4>(P, hl, lane);
+    scan_step_up<8>(P, hl, lane);
+    scan_step_up<16>(P, hl, lane);
     float h = __shfl_up_sync(0xffffffffu, hl, 1);
     if (lane == 0) h = cin;
-    if (lane == 31) my_carry[n] = hl;          // state at the end of this chunk
+    if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
     if (!STATE_ONLY) {
-      const unsigned char* rowp = tile_b + (N + n) * (kChunk * 4);
-      float cv[kTok];
+      const uint32_t rowp = tile_s + (N + n) * (kChunk * 4);
+      float4 cq[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 q = *reinterpret_cast<const float4*>(rowp + poff[k]);
-        cv[4 * k + 0] = q.x; cv[4 * k + 1] = q.y; cv[4 * k + 2] = q.z; cv[4 * k + 3] = q.w;
-      }
+      for (int k = 0; k < 4; ++k) cq[k] = lds128(rowp + poff[k]);
+      // walk the segment in LOGICAL order (physical pieces backwards for a reversed job)
 #pragma unroll
-      for (int i = 0; i < kTok; ++i) {
-        h = fmaf(av[i], h, bv[i]);
-        y[i] = fmaf(cv[phys(i)], h, y[i]);
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = REV ? 3 - kk : kk;
+        const float ce[4] = {cq[k].x, cq[k].y, cq[k].z, cq[k].w};
+#pragma unroll
+        for (int ee = 0; ee < 4; ++ee) {
+          const int e = REV ? 3 - ee : ee;
+          const int i = REV ? kTok - 1 - (4 * k + e) : 4 * k + e;
+          h = fmaf(av[i], h, bv[i]);
+          y[i] = fmaf(ce[e], h, y[i]);
+        }
       }
     }
   }
@@ -154,7 +159,7 @@ __device__ __forceinline__ void scan_chunk(
     float zs[kTok], o[kTok];
     load_vec<T, kTok>(zrow + tseg, zs);
 #pragma unroll
-    for (int i = 0; i < kTok; ++i) o[phys(i)] = y[i] * silu(zs[phys(i)]);
+    for (int i = 0; i < kTok; ++i) o[phys(i)] = y[i] * silu_io<T>(zs[phys(i)]);
     if (!TAIL || tseg + kTok <= L) {
       store_vec<T, kTok>(orow + tseg, o);
     } else {

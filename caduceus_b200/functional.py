@@ -198,6 +198,7 @@ def add_norm(x, weight, bias=None, residual=None, eps=1e-5, is_rms=True, prenorm
 # BiMamba inner path
 # =====================================================================================================
 _JOB_CACHE = {}
+_JOB_ADJACENT = {}
 
 
 def job_tables(nbatch, nstrand, ndir, untied_in, device):
@@ -221,6 +222,10 @@ def job_tables(nbatch, nstrand, ndir, untied_in, device):
                 rev.append(d ^ s)
     t = tuple(torch.tensor(v, dtype=torch.int32, device=device) for v in (seq, pset, rev))
     _JOB_CACHE[key] = t
+    # host-side fact used by the backward: are the jobs of one in-proj output adjacent and equally many?
+    nseq = nbatch * nstrand * nw
+    _JOB_ADJACENT[t[0].data_ptr()] = (len(seq) % nseq == 0 and
+                                      seq == [j // (len(seq) // nseq) for j in range(len(seq))])
     return t
 
 
@@ -381,10 +386,17 @@ class _BiMambaCoreFn(torch.autograd.Function):
         du_total = torch.baddbmm(du, wx_job.transpose(1, 2), dxdbl)
         dx, dconv_w, dconv_b = conv_silu_bwd(xz, du_total, conv_w4, conv_b, jobs, L)
         # several jobs (directions) may share one in-proj output: sum their gradients
-        dxz = torch.zeros(xz.shape, device=xz.device, dtype=torch.float32 if xz.dtype == torch.float32 else act)
         E = dx.shape[1]
-        dxz[:, :E].index_add_(0, seq_l, dx)
-        dxz[:, E:].index_add_(0, seq_l, dz)
+        nseq, njobs = xz.shape[0], dx.shape[0]
+        if njobs == nseq:                                   # one job per in-proj output (untied or unidirectional)
+            dxz = torch.cat([dx, dz], dim=1)
+        elif njobs % nseq == 0 and _JOB_ADJACENT.get(jobs[0].data_ptr(), False):
+            k = njobs // nseq                               # tied projections: the k directions of a sequence are adjacent
+            dxz = torch.cat([dx.view(nseq, k, E, ld).sum(1), dz.view(nseq, k, E, ld).sum(1)], dim=1)
+        else:
+            dxz = torch.zeros(xz.shape, device=xz.device, dtype=act)
+            dxz[:, :E].index_add_(0, seq_l, dx)
+            dxz[:, E:].index_add_(0, seq_l, dz)
         dxz[..., L:] = 0
         return (dxz, dw_x.to(w_x.dtype), dw_dt.to(w_dt.dtype), dconv_w, dconv_b, ddt_b, dA2, dD, None, None)
 
