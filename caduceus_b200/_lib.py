@@ -75,6 +75,14 @@ class ConvBwdArgs(C.Structure):
                 ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32)]
 
 
+class ConvXprojArgs(C.Structure):
+    _fields_ = [("xz", _p), ("w_x", _p), ("w_dt", _p), ("conv_w", _p), ("conv_b", _p),
+                ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
+                ("delta", _p), ("bc", _p),
+                ("L", _i64), ("E", _i64), ("N", _i64), ("R", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64),
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32)]
+
+
 class ConvFwdArgs(C.Structure):
     _fields_ = [("xz", _p), ("u", _p), ("conv_w", _p), ("conv_b", _p),
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
@@ -97,6 +105,7 @@ SYMBOLS = {
     "cad_conv_silu_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), _p]),
     "cad_bimamba_scan_bwd": (C.c_int, [C.POINTER(ScanBwdArgs), _p]),
     "cad_conv_silu_bwd": (C.c_int, [C.POINTER(ConvBwdArgs), _p]),
+    "cad_conv_xproj_fwd": (C.c_int, [C.POINTER(ConvXprojArgs), _p]),
     "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),
 }
 

@@ -244,6 +244,32 @@ def conv_silu(xz, conv_w4, conv_b, jobs, L, halo=None):
     return u
 
 
+def conv_xproj_supported(xz, N, R):
+    E = xz.shape[1] // 2
+    return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 1024
+
+
+def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None):
+    """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores: returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32)
+    without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    nseq, twoE, ld = xz.shape
+    E = twoE // 2
+    R = w_dt.shape[-1]
+    N = (w_x.shape[1] - R) // 2
+    njobs = seq.numel()
+    ldbc = round_up(max(L, 1), 32)
+    delta = torch.empty(njobs, E, ld, device=xz.device, dtype=xz.dtype)
+    bc = torch.empty(njobs, 2 * N, ldbc, device=xz.device, dtype=torch.float32)
+    a = _lib.ConvXprojArgs(_ptr(xz), _ptr(w_x.contiguous()), _ptr(w_dt.contiguous()), _ptr(conv_w4), _ptr(conv_b),
+                           _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(delta), _ptr(bc),
+                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz))
+    _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
+    _launched()
+    return delta, bc
+
+
 def project_dt_bc(xdbl, dt_w_job, L, N):
     """From x_dbl (njobs, R+2N, ld): dt_raw = W_dt . x_dbl[:R] (a K=R GEMM, io dtype) and the fp32 B/C rows in
     the TMA-friendly pitch (multiple of 32 tokens, zero padded)."""

@@ -18,6 +18,7 @@ from . import functional as CF
 from . import seqshard
 
 _LOG2E = 1.4426950408889634
+_FORCE_UNFUSED_XPROJ = False      # tests flip this to compare the fused tensor-core path with conv + cuBLAS
 
 
 # =====================================================================================================
@@ -256,12 +257,17 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
     halo = None
     if sharded:      # the 3 conv samples that logically precede this shard (one tiny all_gather)
         halo = seqshard.gather_halo(xz[:, :E, :], L, jobs[0], jobs[2], shard).to(act)
-    u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                        # (njobs, E, Lp)
-    wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
-    xdbl = torch.bmm(wx_job, u)                                                           # (njobs, R+2N, Lp)
-    del u
-    wdt_job = dw["w_dt"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_dt"].expand(xdbl.shape[0], -1, -1)
-    delta, bc = CF.project_dt_bc(xdbl, wdt_job, L, N)
+    if CF.conv_xproj_supported(xz, N, m0.dt_rank) and not _FORCE_UNFUSED_XPROJ:
+        # one tensor-core kernel: conv+SiLU -> x_proj -> dt_proj; u never touches HBM
+        delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo)
+    else:
+        u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                    # (njobs, E, Lp)
+        wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
+        xdbl = torch.bmm(wx_job, u)                                                       # (njobs, R+2N, Lp)
+        del u
+        wdt_job = (dw["w_dt"].index_select(0, jobs[1].long()) if ndir > 1
+                   else dw["w_dt"].expand(xdbl.shape[0], -1, -1))
+        delta, bc = CF.project_dt_bc(xdbl, wdt_job, L, N)
 
     # ---- fused scan --------------------------------------------------------------------------------------
     h0 = None

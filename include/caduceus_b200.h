@@ -182,6 +182,24 @@ typedef struct {
 } cad_conv_bwd_args;
 int cad_conv_silu_bwd(const cad_conv_bwd_args* a, void* stream);
 
+/* ---- fused conv + SiLU -> x_proj -> dt_proj (tensor cores, 16-bit I/O): produces exactly the operands of
+ *      cad_bimamba_scan_fwd without materialising u = silu(conv(x)).  Replaces causal_conv1d_fwd + the x_proj and
+ *      dt_proj GEMMs of upstream's mamba_inner_fn.
+ *        w_x (P, R+2N, E), w_dt (P, E, R) in the io dtype;  delta (njobs, E, ldd) io dtype;
+ *        bc (njobs, 2N, ldbc) fp32, written for every column < ldbc (zeros beyond L).
+ *      Constraints: io dtype f16/bf16, N == 16, R <= 16, E % 64 == 0; otherwise use cad_conv_silu_fwd + GEMMs.   */
+typedef struct {
+  const void* xz; const void* w_x; const void* w_dt;
+  const float* conv_w; const float* conv_b;
+  const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;
+  const void* halo;
+  void* delta; float* bc;
+  int64_t L, E, N, R;
+  int64_t ldxz, ldd, ldbc;
+  int32_t nseq, njobs, io_dtype;
+} cad_conv_xproj_args;
+int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
+
 /* v1 helper: u = silu(conv(x)) materialised per job for the x_proj GEMM  (njobs, E, ldu). */
 typedef struct {
   const void* xz; void* u;

@@ -34,7 +34,8 @@ def test_struct_sizes_match_header_layout():
     for cname, cls in (("cad_embedding_args", _lib.EmbeddingArgs), ("cad_add_norm_args", _lib.AddNormArgs),
                        ("cad_scan_fwd_args", _lib.ScanFwdArgs), ("cad_conv_fwd_args", _lib.ConvFwdArgs),
                        ("cad_add_norm_bwd_args", _lib.AddNormBwdArgs), ("cad_embedding_bwd_args", _lib.EmbeddingBwdArgs),
-                       ("cad_scan_bwd_args", _lib.ScanBwdArgs), ("cad_conv_bwd_args", _lib.ConvBwdArgs)):
+                       ("cad_scan_bwd_args", _lib.ScanBwdArgs), ("cad_conv_bwd_args", _lib.ConvBwdArgs),
+                       ("cad_conv_xproj_args", _lib.ConvXprojArgs)):
         names = []
         for decl in structs[cname].split(";"):
             for part in decl.split(","):
