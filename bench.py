@@ -305,8 +305,16 @@ def run_b200(a):
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
         achieved = bytes_per_launch / (avg_scan_ms * 1e-3) / 1e9 if scan_ms else None
+        traffic = None        # measured DRAM bytes per launch, from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+            if a.seqlen == 131072 and a.d_model == 256 and a.batch == 1 and not shard_seq:
+                traffic = tj[a.model]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "bimamba_scan_fwd_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "6.65 TB/s (of fallback)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_scan_ms,
                 "launches_timed": len(scan_ms), "share_of_step": avg_scan_ms * len(scan_ms) / ms_dev if scan_ms else None}

@@ -55,6 +55,14 @@ class ScanFwdArgs(C.Structure):
                 ("state_only", _i32)]
 
 
+class ScanFixupArgs(C.Structure):
+    _fields_ = [("xz", _p), ("delta", _p), ("bc", _p), ("out", _p), ("dt_b", _p), ("A2", _p),
+                ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("h0", _p),
+                ("L", _i64), ("E", _i64), ("N", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
+                ("cutoff_log2", _f32)]
+
+
 class ScanBwdArgs(C.Structure):
     _fields_ = [("xz", _p), ("delta", _p), ("bc", _p), ("dout", _p),
                 ("conv_w", _p), ("conv_b", _p), ("dt_b", _p), ("A2", _p), ("Dskip", _p),
@@ -104,6 +112,7 @@ SYMBOLS = {
     "cad_scan_chunk_len": (C.c_int, []),
     "cad_conv_silu_fwd": (C.c_int, [C.POINTER(ConvFwdArgs), _p]),
     "cad_bimamba_scan_bwd": (C.c_int, [C.POINTER(ScanBwdArgs), _p]),
+    "cad_bimamba_scan_fixup": (C.c_int, [C.POINTER(ScanFixupArgs), _p]),
     "cad_conv_silu_bwd": (C.c_int, [C.POINTER(ConvBwdArgs), _p]),
     "cad_conv_xproj_fwd": (C.c_int, [C.POINTER(ConvXprojArgs), _p]),
     "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),

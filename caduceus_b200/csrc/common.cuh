@@ -84,6 +84,20 @@ __device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&v)[V])
   }
 }
 
+// same, from shared memory (plain loads; __ldg is for global memory only)
+template <typename T, int V>
+__device__ __forceinline__ void load_vec_smem(const T* p, float (&v)[V]) {
+  static_assert(V % 8 == 0, "V must be a multiple of 8");
+  constexpr int EPV = 16 / sizeof(T);
+#pragma unroll
+  for (int i = 0; i < V / EPV; ++i) {
+    const uint4 raw = reinterpret_cast<const uint4*>(p)[i];
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < EPV; ++k) v[i * EPV + k] = io<T>::to_f(e[k]);
+  }
+}
+
 template <typename T, int V>
 __device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&v)[V]) {
   static_assert(V % 8 == 0, "V must be a multiple of 8");

@@ -31,7 +31,14 @@ struct ScanSmem {
   float* carry;      // kMaxG x N   running state of each warp's channel
   float* a2;         // kMaxG x N   A2 of each warp's channel
   uint64_t* bar;     // TMA completion barrier
+  unsigned char* pre; // [2][G][3][512] x / dt_raw / z segments of the current and the next chunk (16-bit I/O only)
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // One chunk of one channel.  TAIL: the chunk straddles the sequence end (per-token masks, halo in the pad).
 template <typename T, int N, bool REV, bool TAIL, bool STATE_ONLY>
@@ -40,7 +47,7 @@ __device__ __forceinline__ void scan_chunk(
     const T* __restrict__ xrow, const T* __restrict__ zrow, const T* __restrict__ drow, T* __restrict__ orow,
     int64_t tseg, bool active, const float (&cw)[4], float cb, float dtb, float Dk, const float (&hal)[3],
     float (&prev3)[3], float& dt_total, float* my_carry, const float* my_a2, uint32_t parity, bool issue_next,
-    const CUtensorMap* tmap, int next_c1, int job_row) {
+    const CUtensorMap* tmap, int next_c1, int job_row, const T* pre_cur, T* pre_next, int64_t tseg_next) {
   constexpr int EPV = 16 / sizeof(T);
   const int64_t L = a.L;
   auto phys = [](int i) { return REV ? kTok - 1 - i : i; };
@@ -48,13 +55,29 @@ __device__ __forceinline__ void scan_chunk(
   const bool seg_in = !TAIL || tseg < L;
 
   // ---- 1. x and dt_raw segments (global -> registers) ------------------------------------------------
+  constexpr bool PRE = sizeof(T) == 2;     // 16-bit I/O: segments were staged by cp.async one chunk ahead
   float xs[kTok], dr[kTok];
   if (seg_in) {
-    load_vec<T, kTok>(xrow + tseg, xs);
-    load_vec<T, kTok>(drow + tseg, dr);
+    if (PRE) {
+      cp_async_wait_all();                 // my own copies (only this lane reads what it staged)
+      load_vec_smem<T, kTok>(pre_cur, xs);
+      load_vec_smem<T, kTok>(pre_cur + kChunk, dr);
+    } else {
+      load_vec<T, kTok>(xrow + tseg, xs);
+      load_vec<T, kTok>(drow + tseg, dr);
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < kTok; ++i) { xs[i] = 0.f; dr[i] = 0.f; }
+  }
+  if (PRE && issue_next && tseg_next < L) {   // stream in the next chunk's x / dt_raw / z behind this chunk's math
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      cp_async16(pre_next + 8 * v, xrow + tseg_next + 8 * v);
+      cp_async16(pre_next + kChunk + 8 * v, drow + tseg_next + 8 * v);
+      if (!STATE_ONLY) cp_async16(pre_next + 2 * kChunk + 8 * v, zrow + tseg_next + 8 * v);
+    }
+    cp_async_commit();
   }
 
   // ---- 2. per-(token, channel) prologue: conv + SiLU, dt, dt*u (independent of the tile) -------------
@@ -157,7 +180,8 @@ __device__ __forceinline__ void scan_chunk(
   // ---- 5. gate with silu(z) and store (physical order) ---------------------------------------------------
   if (!STATE_ONLY && seg_in && active) {
     float zs[kTok], o[kTok];
-    load_vec<T, kTok>(zrow + tseg, zs);
+    if (PRE) load_vec_smem<T, kTok>(pre_cur + 2 * kChunk, zs);
+    else load_vec<T, kTok>(zrow + tseg, zs);
 #pragma unroll
     for (int i = 0; i < kTok; ++i) o[phys(i)] = y[i] * silu_io<T>(zs[phys(i)]);
     if (!TAIL || tseg + kTok <= L) {
@@ -231,6 +255,24 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     tma_load_3d(sm.tile, tmap, 0, (int)(first * blocks_per_chunk), job_row, sm.bar);
   }
 
+  // 16-bit I/O: this lane's x / dt_raw / z segments are staged in smem one chunk ahead (cp.async, no registers held)
+  constexpr bool PRE = sizeof(T) == 2;
+  T* pre_base = reinterpret_cast<T*>(sm.pre);
+  auto pre_ptr = [&](int buf) { return pre_base + ((size_t)(buf * G + warp) * 3) * kChunk + seg * kTok; };
+  if (PRE && nchunks > 0) {
+    const int64_t ts0 = (REV ? nchunks - 1 : 0) * kChunk + (int64_t)seg * kTok;
+    if (ts0 < L) {
+      T* d = pre_ptr(0);
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        cp_async16(d + 8 * v, xrow + ts0 + 8 * v);
+        cp_async16(d + kChunk + 8 * v, drow + ts0 + 8 * v);
+        if (!STATE_ONLY) cp_async16(d + 2 * kChunk + 8 * v, zrow + ts0 + 8 * v);
+      }
+      cp_async_commit();
+    }
+  }
+
   uint32_t parity = 0;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int64_t pcidx = REV ? nchunks - 1 - c : c;
@@ -238,12 +280,17 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     const bool issue_next = c + 1 < nchunks;
     const int next_c1 = (int)((REV ? pcidx - 1 : pcidx + 1) * blocks_per_chunk);
     const bool tail = (pcidx + 1) * kChunk > L;
+    const int64_t tseg_next = (REV ? pcidx - 1 : pcidx + 1) * kChunk + (int64_t)seg * kTok;
+    const T* pre_cur = pre_ptr((int)(c & 1));
+    T* pre_next = pre_ptr((int)((c + 1) & 1));
     if (tail)
       scan_chunk<T, N, REV, true, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
-                                  prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row);
+                                  prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
+                                  tseg_next);
     else
       scan_chunk<T, N, REV, false, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
-                                   prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row);
+                                   prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
+                                   tseg_next);
     parity ^= 1;
     if (a.chunk_state) {
       __syncwarp();
@@ -273,6 +320,7 @@ bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUten
   sm.carry = reinterpret_cast<float*>(base + (size_t)2 * N * kChunk * 4);
   sm.a2 = sm.carry + kMaxG * N;
   sm.bar = reinterpret_cast<uint64_t*>(sm.a2 + kMaxG * N);
+  sm.pre = reinterpret_cast<unsigned char*>(sm.bar + 2);
   if (threadIdx.x == 0) mbar_init(sm.bar, 1);
   const int job = blockIdx.y;
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
@@ -285,7 +333,8 @@ static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
   CUtensorMap tmap;
   if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * N, a.ldbc, a.L, 2 * N) != 0) return -1;
 
-  const size_t smem = 1024 + (size_t)2 * N * kChunk * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16;
+  const size_t pre_bytes = sizeof(T) == 2 ? (size_t)2 * G * 3 * kChunk * sizeof(T) : 0;
+  const size_t smem = 1024 + (size_t)2 * N * kChunk * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16 + pre_bytes;
   auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, true> : bimamba_scan_fwd_kernel<T, N, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

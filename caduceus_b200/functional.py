@@ -318,6 +318,23 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     return out, hlast, dtsum, cstate
 
 
+def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, channels_per_cta=0):
+    """In place: out += silu(z) * sum_n C * exp2(A2 * cumsum(dt)) * h0 — turns a zero-carry shard scan into the scan
+    with carry-in h0 (njobs, E, N).  See csrc/scan_fixup.cu."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    _, _, dt_b, A2, _ = packed
+    nseq, twoE, ldxz = xz.shape
+    E = twoE // 2
+    njobs, twoN, ldbc = bc.shape
+    a = _lib.ScanFixupArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
+                           _ptr(rev), _ptr(h0.contiguous()), L, E, twoN // 2, ldxz, delta.stride(1), ldbc, out.stride(1),
+                           nseq, njobs, _dt(xz), channels_per_cta, float(cutoff_log2))
+    _lib.check(lib.cad_bimamba_scan_fixup(C.byref(a), _stream()), "cad_bimamba_scan_fixup")
+    _launched()
+    return out
+
+
 def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None, want_dh0=False,
              channels_per_cta=0):
     """Backward of scan_fwd: returns dz, du (scan path), ddelta (io dtype), dbc (fp32), ddt_b, dA2, dD, dh0."""

@@ -270,11 +270,14 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
         delta, bc = CF.project_dt_bc(xdbl, wdt_job, L, N)
 
     # ---- fused scan --------------------------------------------------------------------------------------
-    h0 = None
-    if sharded:      # zero-carry pass -> all_gather(H, sum dt) -> compose this shard's carry-in (seqshard.py)
-        _, hl, ds, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, state_only=True)
+    if not sharded:
+        yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L)
+    else:
+        # zero-carry scan (outputs + end state + sum dt) -> ONE all_gather -> compose this shard's carry-in ->
+        # add its decaying contribution in place (seqshard.py, csrc/scan_fixup.cu).  Ranks never wait for each other.
+        yg, hl, ds, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True)
         h0 = seqshard.gather_carry(hl, ds, packed[3], jobs[1], jobs[2], shard)
-    yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, h0=h0)
+        CF.scan_fixup(xz, delta, bc, yg, packed, jobs, L, h0)
     del xz
 
     # ---- out_proj -------------------------------------------------------------------------------------------

@@ -148,6 +148,22 @@ typedef struct {
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
 
+/* ---- carry fix-up of a sequence-sharded scan: adds, in place, the contribution of the carry-in
+ *      state h0 to an output that was produced by cad_bimamba_scan_fwd with a ZERO carry:
+ *          out[tau] += silu(z[tau]) * sum_n C[tau,n] * exp2(A2[n] * sum_{s<=tau} dt[s]) * h0[n]
+ *      (channel, state) pairs are dropped once A2*cumdt < cutoff_log2; CTAs stop when nothing is left to add.   */
+typedef struct {
+  const void* xz; const void* delta; const float* bc; void* out;
+  const float* dt_b; const float* A2;
+  const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;
+  const float* h0;          /* (njobs, E, N) carry-in state */
+  int64_t L, E, N;
+  int64_t ldxz, ldd, ldbc, ldo;
+  int32_t nseq, njobs, io_dtype, channels_per_cta;
+  float   cutoff_log2;      /* e.g. -40: terms below 2^-40 * |C h0| are dropped */
+} cad_scan_fixup_args;
+int cad_bimamba_scan_fixup(const cad_scan_fixup_args* a, void* stream);
+
 /* ---- backward of cad_bimamba_scan_fwd (replaces selective_scan_cuda.bwd).
  *      Inputs as the forward plus dout (njobs, E, ldo) and the forward's chunk_state.  Outputs:
  *        dz      (njobs, E, lddz)   gradient of the gate input z                               io dtype
