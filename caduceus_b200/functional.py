@@ -199,6 +199,7 @@ def add_norm(x, weight, bias=None, residual=None, eps=1e-5, is_rms=True, prenorm
 # =====================================================================================================
 _JOB_CACHE = {}
 _JOB_ADJACENT = {}
+JOB_HOST = {}
 
 
 def job_tables(nbatch, nstrand, ndir, untied_in, device):
@@ -226,6 +227,7 @@ def job_tables(nbatch, nstrand, ndir, untied_in, device):
     nseq = nbatch * nstrand * nw
     _JOB_ADJACENT[t[0].data_ptr()] = (len(seq) % nseq == 0 and
                                       seq == [j // (len(seq) // nseq) for j in range(len(seq))])
+    JOB_HOST[t[0].data_ptr()] = (tuple(seq), tuple(pset), tuple(rev))      # host copies: no device sync to read them
     return t
 
 

@@ -9,12 +9,15 @@ sequence, all channels; weights are replicated.  Everything on the path is token
 
 A literal "send h_end to the next rank" chain serialises the ranks (rank k cannot finish before rank k-1).  The
 recurrence is affine in the carried state, so instead every rank
-   1. scans its shard from a ZERO state (scan kernel in `state_only` mode) -> zero-carry end state H_k and
+   1. scans its shard from a ZERO state, producing the outputs of that zero-carry scan plus the end state H_k and
       sum(dt)_k, from which the shard's total decay is P_k = exp2(A2 * sum(dt)_k);
    2. takes part in ONE small all_gather of (H, sum dt) — 2 x (32 KiB + 2 KiB) per job —
    3. composes its true carry-in  h0_k = sum_{j<k} (prod_{j<i<k} P_i) H_j  locally (reversed order for reversed jobs),
-   4. scans again from h0_k, now producing the outputs.
-Both scans are shard-local, so the P ranks run concurrently: time per layer ~ 2 * T_scan(L / P).
+   4. adds the contribution of h0_k to its outputs in place:  silu(z) * sum_n C * exp2(A2 * cumsum(dt)) * h0
+      (csrc/scan_fixup.cu) — a term that only decays along the shard, so it is cut off per (channel, state) once it is
+      below 2^-40 and typically touches a few percent of the shard.
+All scans are shard-local and start together, so the P ranks run concurrently: time per layer ~ T_scan(L / P) * (1 + eps).
+Measured on 2 x B200 (L = 131072, D = 256, 16 layers, bf16 forward): PS 50.8 -> 32.7 ms, Ph 37.6 -> 23.2 ms.
 
 `sequence_parallel(group)` is the user-facing switch: inside it `bimamba_inner` (hence every Caduceus model of this
 package) treats its input as the local shard.
@@ -63,7 +66,10 @@ def gather_halo(x_rows, L, seq_of_job, rev_of_job, ctx):
     allv = _all_gather(edges, ctx)                                              # (world, 2, nseq, E, 3)
     zero = torch.zeros_like(edges[0, 0])
     halos = []
-    for s, r in zip(seq_of_job.tolist(), rev_of_job.tolist()):
+    from . import functional as CF
+    host = CF.JOB_HOST.get(seq_of_job.data_ptr())
+    seq_l, rev_l = (host[0], host[2]) if host is not None else (seq_of_job.tolist(), rev_of_job.tolist())
+    for s, r in zip(seq_l, rev_l):
         if not r:      # left-to-right: predecessor rank's LAST three samples, already in logical order
             halos.append(allv[ctx.rank - 1, 1, s] if ctx.rank > 0 else zero)
         else:          # right-to-left: successor rank's FIRST three, logical order = physical order reversed
