@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: MLM step = forward + loss + backward + AdamW under bf16 autocast (BASELINE configs[3] on 1 GPU)")
+    ap.add_argument("--scan-tok", type=int, default=0, choices=[0, 8, 16], help="tokens per lane of the scan kernel (tuning)")
     ap.add_argument("--shard", default="none", choices=["none", "seq"],
                     help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
     return ap.parse_args()
@@ -165,6 +166,7 @@ def run_b200(a):
     import caduceus
     from caduceus_b200 import functional as CF
 
+    CF.SCAN_TOKENS_PER_LANE = a.scan_tok
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -65,12 +65,14 @@ __device__ __forceinline__ void scan_step_up(float& P, float& H, int lane) {
       : "+f"(H), "+f"(P) : "f"(Hp), "f"(Pp), "r"(lane), "n"(OFF));
 }
 
-// this lane's four 16-byte pieces inside a TMA-swizzled tile row (see scan_fwd.cu): SWIZZLE_128B stores 16-byte
-// chunk c of 128-byte line l at chunk position c ^ (l & 7); a tile row is 16 consecutive lines.
-__device__ __forceinline__ void tile_piece_offsets(int seg, uint32_t (&poff)[4]) {
-  const int blk = seg >> 1, c0 = 4 * (seg & 1);
+// this lane's TOK/4 16-byte pieces inside a TMA-swizzled tile row (see scan_fwd.cu): SWIZZLE_128B stores 16-byte
+// chunk c of 128-byte line l at chunk position c ^ (l & 7); a tile row is CH/32 consecutive lines (line = 32 tokens).
+template <int TOK = kTok>
+__device__ __forceinline__ void tile_piece_offsets(int seg, uint32_t (&poff)[TOK / 4]) {
+  constexpr int SPB = 32 / TOK;                 // lane segments per 32-token line
+  const int blk = seg / SPB, c0 = (TOK / 4) * (seg % SPB);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) poff[k] = blk * 128 + (((c0 + k) ^ (blk & 7)) << 4);
+  for (int k = 0; k < TOK / 4; ++k) poff[k] = blk * 128 + (((c0 + k) ^ (blk & 7)) << 4);
 }
 
 // ---- host: tensor map over a (nrows, ld) fp32 matrix viewed as (32 tokens, blocks, rows) ----------------------
@@ -90,15 +92,15 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// rows_per_box rows x 512 tokens per TMA; blocks past ceil(L/32) are out of bounds -> zero-filled.
+// rows_per_box rows x chunk_tokens tokens per TMA; blocks past ceil(L/32) are out of bounds -> zero-filled.
 inline int make_row_tile_map(CUtensorMap* tmap, const float* base, int64_t nrows, int64_t ld, int64_t L,
-                             int rows_per_box) {
+                             int rows_per_box, int chunk_tokens = kChunk) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return -1; }
   const cuuint64_t nblk = (cuuint64_t)((L + kBlkTok - 1) / kBlkTok);
   const cuuint64_t dims[3] = {(cuuint64_t)kBlkTok, nblk, (cuuint64_t)nrows};
   const cuuint64_t strides[2] = {(cuuint64_t)kBlkTok * 4, (cuuint64_t)ld * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)kBlkTok, (cuuint32_t)(kChunk / kBlkTok), (cuuint32_t)rows_per_box};
+  const cuuint32_t box[3] = {(cuuint32_t)kBlkTok, (cuuint32_t)(chunk_tokens / kBlkTok), (cuuint32_t)rows_per_box};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

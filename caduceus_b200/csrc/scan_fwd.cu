@@ -41,52 +41,53 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // One chunk of one channel.  TAIL: the chunk straddles the sequence end (per-token masks, halo in the pad).
-template <typename T, int N, bool REV, bool TAIL, bool STATE_ONLY>
+template <typename T, int N, int TOK, bool REV, bool TAIL, bool STATE_ONLY>
 __device__ __forceinline__ void scan_chunk(
-    const cad_scan_fwd_args& a, const ScanSmem& sm, int lane, int seg, const uint32_t (&poff)[4],
+    const cad_scan_fwd_args& a, const ScanSmem& sm, int lane, int seg, const uint32_t (&poff)[TOK / 4],
     const T* __restrict__ xrow, const T* __restrict__ zrow, const T* __restrict__ drow, T* __restrict__ orow,
     int64_t tseg, bool active, const float (&cw)[4], float cb, float dtb, float Dk, const float (&hal)[3],
     float (&prev3)[3], float& dt_total, float* my_carry, const float* my_a2, uint32_t parity, bool issue_next,
     const CUtensorMap* tmap, int next_c1, int job_row, const T* pre_cur, T* pre_next, int64_t tseg_next) {
+  constexpr int CH = 32 * TOK;         // tokens per chunk
   constexpr int EPV = 16 / sizeof(T);
   const int64_t L = a.L;
-  auto phys = [](int i) { return REV ? kTok - 1 - i : i; };
+  auto phys = [](int i) { return REV ? TOK - 1 - i : i; };
   auto halo_at = [&](int64_t tau) { return tau == -1 ? hal[2] : (tau == -2 ? hal[1] : (tau == -3 ? hal[0] : 0.f)); };
   const bool seg_in = !TAIL || tseg < L;
 
   // ---- 1. x and dt_raw segments (global -> registers) ------------------------------------------------
   constexpr bool PRE = sizeof(T) == 2;     // 16-bit I/O: segments were staged by cp.async one chunk ahead
-  float xs[kTok], dr[kTok];
+  float xs[TOK], dr[TOK];
   if (seg_in) {
     if (PRE) {
       cp_async_wait_all();                 // my own copies (only this lane reads what it staged)
-      load_vec_smem<T, kTok>(pre_cur, xs);
-      load_vec_smem<T, kTok>(pre_cur + kChunk, dr);
+      load_vec_smem<T, TOK>(pre_cur, xs);
+      load_vec_smem<T, TOK>(pre_cur + CH, dr);
     } else {
-      load_vec<T, kTok>(xrow + tseg, xs);
-      load_vec<T, kTok>(drow + tseg, dr);
+      load_vec<T, TOK>(xrow + tseg, xs);
+      load_vec<T, TOK>(drow + tseg, dr);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < kTok; ++i) { xs[i] = 0.f; dr[i] = 0.f; }
+    for (int i = 0; i < TOK; ++i) { xs[i] = 0.f; dr[i] = 0.f; }
   }
   if (PRE && issue_next && tseg_next < L) {   // stream in the next chunk's x / dt_raw / z behind this chunk's math
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
+    for (int v = 0; v < TOK / 8; ++v) {
       cp_async16(pre_next + 8 * v, xrow + tseg_next + 8 * v);
-      cp_async16(pre_next + kChunk + 8 * v, drow + tseg_next + 8 * v);
-      if (!STATE_ONLY) cp_async16(pre_next + 2 * kChunk + 8 * v, zrow + tseg_next + 8 * v);
+      cp_async16(pre_next + CH + 8 * v, drow + tseg_next + 8 * v);
+      if (!STATE_ONLY) cp_async16(pre_next + 2 * CH + 8 * v, zrow + tseg_next + 8 * v);
     }
     cp_async_commit();
   }
 
   // ---- 2. per-(token, channel) prologue: conv + SiLU, dt, dt*u (independent of the tile) -------------
-  float dt[kTok], du[kTok], y[kTok];
+  float dt[TOK], du[TOK], y[TOK];
   float dsum = 0.f;
   {
-    float xl[kTok + 3];
+    float xl[TOK + 3];
 #pragma unroll
-    for (int i = 0; i < kTok; ++i) {
+    for (int i = 0; i < TOK; ++i) {
       float v = xs[phys(i)];
       if (TAIL) {
         const int64_t t = tseg + phys(i);
@@ -96,13 +97,13 @@ __device__ __forceinline__ void scan_chunk(
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {        // logical predecessors: previous lane / previous chunk
-      const float up = __shfl_up_sync(0xffffffffu, xl[kTok + k], 1);
+      const float up = __shfl_up_sync(0xffffffffu, xl[TOK + k], 1);
       xl[k] = (lane == 0) ? prev3[k] : up;
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) prev3[k] = __shfl_sync(0xffffffffu, xl[kTok + k], 31);
+    for (int k = 0; k < 3; ++k) prev3[k] = __shfl_sync(0xffffffffu, xl[TOK + k], 31);
 #pragma unroll
-    for (int i = 0; i < kTok; ++i) {
+    for (int i = 0; i < TOK; ++i) {
       const float u = silu_io<T>(cb + cw[0] * xl[i] + cw[1] * xl[i + 1] + cw[2] * xl[i + 2] + cw[3] * xl[i + 3]);
       float d = softplus(dr[phys(i)] + dtb);
       if (TAIL && tseg + phys(i) >= L) d = 0.f;     // masked token: a = 1, b = 0 -> state passes through
@@ -122,23 +123,23 @@ __device__ __forceinline__ void scan_chunk(
   for (int n = 0; n < N; ++n) {
     const float A2n = lds32(a2_s + 4 * n);
     const float cin = lds32(carry_s + 4 * n);
-    float av[kTok], bv[kTok];
+    float av[TOK], bv[TOK];
     float hl = (lane == 0) ? cin : 0.f;
     {
-      const uint32_t rowp = tile_s + n * (kChunk * 4);
+      const uint32_t rowp = tile_s + n * (CH * 4);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < TOK / 4; ++k) {
         const float4 q = lds128(rowp + poff[k]);
         const float bq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int i = REV ? kTok - 1 - (4 * k + e) : 4 * k + e;     // logical item of physical token 4k+e
+          const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;     // logical item of physical token 4k+e
           av[i] = ex2(dt[i] * A2n);
           bv[i] = du[i] * bq[e];
         }
       }
 #pragma unroll
-      for (int i = 0; i < kTok; ++i) hl = fmaf(av[i], hl, bv[i]);
+      for (int i = 0; i < TOK; ++i) hl = fmaf(av[i], hl, bv[i]);
     }
     float P = ex2(A2n * dsum);
     scan_step_up<1>(P, hl, lane);
@@ -150,19 +151,19 @@ __device__ __forceinline__ void scan_chunk(
     if (lane == 0) h = cin;
     if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
     if (!STATE_ONLY) {
-      const uint32_t rowp = tile_s + (N + n) * (kChunk * 4);
-      float4 cq[4];
+      const uint32_t rowp = tile_s + (N + n) * (CH * 4);
+      float4 cq[TOK / 4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) cq[k] = lds128(rowp + poff[k]);
+      for (int k = 0; k < TOK / 4; ++k) cq[k] = lds128(rowp + poff[k]);
       // walk the segment in LOGICAL order (physical pieces backwards for a reversed job)
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = REV ? 3 - kk : kk;
+      for (int kk = 0; kk < TOK / 4; ++kk) {
+        const int k = REV ? TOK / 4 - 1 - kk : kk;
         const float ce[4] = {cq[k].x, cq[k].y, cq[k].z, cq[k].w};
 #pragma unroll
         for (int ee = 0; ee < 4; ++ee) {
           const int e = REV ? 3 - ee : ee;
-          const int i = REV ? kTok - 1 - (4 * k + e) : 4 * k + e;
+          const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;
           h = fmaf(av[i], h, bv[i]);
           y[i] = fmaf(ce[e], h, y[i]);
         }
@@ -173,31 +174,32 @@ __device__ __forceinline__ void scan_chunk(
   // ---- 4. hand the tile back: everyone is done reading -> request the next chunk -------------------------
   __syncthreads();
   if (issue_next && threadIdx.x == 0) {
-    mbar_expect_tx(sm.bar, 2 * N * kChunk * 4);
+    mbar_expect_tx(sm.bar, 2 * N * CH * 4);
     tma_load_3d(sm.tile, tmap, 0, next_c1, job_row, sm.bar);
   }
 
   // ---- 5. gate with silu(z) and store (physical order) ---------------------------------------------------
   if (!STATE_ONLY && seg_in && active) {
-    float zs[kTok], o[kTok];
-    if (PRE) load_vec_smem<T, kTok>(pre_cur + 2 * kChunk, zs);
-    else load_vec<T, kTok>(zrow + tseg, zs);
+    float zs[TOK], o[TOK];
+    if (PRE) load_vec_smem<T, TOK>(pre_cur + 2 * CH, zs);
+    else load_vec<T, TOK>(zrow + tseg, zs);
 #pragma unroll
-    for (int i = 0; i < kTok; ++i) o[phys(i)] = y[i] * silu_io<T>(zs[phys(i)]);
-    if (!TAIL || tseg + kTok <= L) {
-      store_vec<T, kTok>(orow + tseg, o);
+    for (int i = 0; i < TOK; ++i) o[phys(i)] = y[i] * silu_io<T>(zs[phys(i)]);
+    if (!TAIL || tseg + TOK <= L) {
+      store_vec<T, TOK>(orow + tseg, o);
     } else {
 #pragma unroll
-      for (int i = 0; i < kTok; ++i)
+      for (int i = 0; i < TOK; ++i)
         if (tseg + i < L) orow[tseg + i] = io<T>::from_f(o[i]);
     }
   }
   (void)EPV;
 }
 
-template <typename T, int N, bool REV, bool STATE_ONLY>
+template <typename T, int N, int TOK, bool REV, bool STATE_ONLY>
 __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUtensorMap* tmap, int job, int seq,
                                          int pset, const ScanSmem& sm) {
+  constexpr int CH = 32 * TOK;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int G = blockDim.x >> 5;
@@ -205,7 +207,7 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
   const int64_t ch = (int64_t)blockIdx.x * G + warp;
   const bool active = ch < E;                  // tail CTA: idle warps only keep the barriers company
   const int64_t chc = active ? ch : E - 1;
-  const int64_t nchunks = (L + kChunk - 1) / kChunk;
+  const int64_t nchunks = (L + CH - 1) / CH;
 
   const T* __restrict__ xrow = static_cast<const T*>(a.xz) + ((int64_t)seq * 2 * E + chc) * a.ldxz;
   const T* __restrict__ zrow = xrow + E * a.ldxz;
@@ -230,7 +232,7 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     const T* hp = static_cast<const T*>(a.halo) + ((int64_t)job * E + chc) * 3;
     hal[0] = io<T>::to_f(hp[0]); hal[1] = io<T>::to_f(hp[1]); hal[2] = io<T>::to_f(hp[2]);
   }
-  const int64_t tau0 = REV ? L - nchunks * kChunk : 0;      // logical time of the first item of chunk 0 (<= 0)
+  const int64_t tau0 = REV ? L - nchunks * CH : 0;      // logical time of the first item of chunk 0 (<= 0)
   float prev3[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -243,31 +245,31 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
   // TMA SWIZZLE_128B stores 16-byte chunk c of 128-byte line l at chunk position c ^ (l & 7); a tile row is 16
   // consecutive lines (line index = row*16 + blk, so l & 7 == blk & 7).
   const int seg = REV ? 31 - lane : lane;
-  uint32_t poff[4];
-  tile_piece_offsets(seg, poff);
+  uint32_t poff[TOK / 4];
+  tile_piece_offsets<TOK>(seg, poff);
   const int job_row = job * 2 * N;
-  const int blocks_per_chunk = kChunk / kBlkTok;
+  const int blocks_per_chunk = CH / kBlkTok;
 
   __syncthreads();                               // barrier init + parameter staging visible
   if (threadIdx.x == 0) {
     const int64_t first = REV ? nchunks - 1 : 0;
-    mbar_expect_tx(sm.bar, 2 * N * kChunk * 4);
+    mbar_expect_tx(sm.bar, 2 * N * CH * 4);
     tma_load_3d(sm.tile, tmap, 0, (int)(first * blocks_per_chunk), job_row, sm.bar);
   }
 
   // 16-bit I/O: this lane's x / dt_raw / z segments are staged in smem one chunk ahead (cp.async, no registers held)
   constexpr bool PRE = sizeof(T) == 2;
   T* pre_base = reinterpret_cast<T*>(sm.pre);
-  auto pre_ptr = [&](int buf) { return pre_base + ((size_t)(buf * G + warp) * 3) * kChunk + seg * kTok; };
+  auto pre_ptr = [&](int buf) { return pre_base + ((size_t)(buf * G + warp) * 3) * CH + seg * TOK; };
   if (PRE && nchunks > 0) {
-    const int64_t ts0 = (REV ? nchunks - 1 : 0) * kChunk + (int64_t)seg * kTok;
+    const int64_t ts0 = (REV ? nchunks - 1 : 0) * CH + (int64_t)seg * TOK;
     if (ts0 < L) {
       T* d = pre_ptr(0);
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
+      for (int v = 0; v < TOK / 8; ++v) {
         cp_async16(d + 8 * v, xrow + ts0 + 8 * v);
-        cp_async16(d + kChunk + 8 * v, drow + ts0 + 8 * v);
-        if (!STATE_ONLY) cp_async16(d + 2 * kChunk + 8 * v, zrow + ts0 + 8 * v);
+        cp_async16(d + CH + 8 * v, drow + ts0 + 8 * v);
+        if (!STATE_ONLY) cp_async16(d + 2 * CH + 8 * v, zrow + ts0 + 8 * v);
       }
       cp_async_commit();
     }
@@ -276,19 +278,19 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
   uint32_t parity = 0;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int64_t pcidx = REV ? nchunks - 1 - c : c;
-    const int64_t tseg = pcidx * kChunk + (int64_t)seg * kTok;
+    const int64_t tseg = pcidx * CH + (int64_t)seg * TOK;
     const bool issue_next = c + 1 < nchunks;
     const int next_c1 = (int)((REV ? pcidx - 1 : pcidx + 1) * blocks_per_chunk);
-    const bool tail = (pcidx + 1) * kChunk > L;
-    const int64_t tseg_next = (REV ? pcidx - 1 : pcidx + 1) * kChunk + (int64_t)seg * kTok;
+    const bool tail = (pcidx + 1) * CH > L;
+    const int64_t tseg_next = (REV ? pcidx - 1 : pcidx + 1) * CH + (int64_t)seg * TOK;
     const T* pre_cur = pre_ptr((int)(c & 1));
     T* pre_next = pre_ptr((int)((c + 1) & 1));
     if (tail)
-      scan_chunk<T, N, REV, true, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, TOK, REV, true, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                   prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
                                   tseg_next);
     else
-      scan_chunk<T, N, REV, false, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, TOK, REV, false, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                    prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
                                    tseg_next);
     parity ^= 1;
@@ -309,33 +311,35 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
   }
 }
 
-template <typename T, int N, bool STATE_ONLY>
-__global__ void __launch_bounds__(kMaxG * 32, 2)
+template <typename T, int N, int TOK, bool STATE_ONLY>
+__global__ void __launch_bounds__(kMaxG * 32, (TOK == 16 ? 2 : 4))
 bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_raw[];
   // the swizzled TMA destination must be 1024-byte aligned
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   ScanSmem sm;
   sm.tile = reinterpret_cast<float*>(base);
-  sm.carry = reinterpret_cast<float*>(base + (size_t)2 * N * kChunk * 4);
+  constexpr int CH = 32 * TOK;
+  sm.carry = reinterpret_cast<float*>(base + (size_t)2 * N * CH * 4);
   sm.a2 = sm.carry + kMaxG * N;
   sm.bar = reinterpret_cast<uint64_t*>(sm.a2 + kMaxG * N);
   sm.pre = reinterpret_cast<unsigned char*>(sm.bar + 2);
   if (threadIdx.x == 0) mbar_init(sm.bar, 1);
   const int job = blockIdx.y;
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
-  if (rev) scan_job<T, N, true, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
-  else     scan_job<T, N, false, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
+  if (rev) scan_job<T, N, TOK, true, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
+  else     scan_job<T, N, TOK, false, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
 }
 
-template <typename T, int N>
+template <typename T, int N, int TOK>
 static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
+  constexpr int CH = 32 * TOK;
   CUtensorMap tmap;
-  if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * N, a.ldbc, a.L, 2 * N) != 0) return -1;
+  if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * N, a.ldbc, a.L, 2 * N, CH) != 0) return -1;
 
-  const size_t pre_bytes = sizeof(T) == 2 ? (size_t)2 * G * 3 * kChunk * sizeof(T) : 0;
-  const size_t smem = 1024 + (size_t)2 * N * kChunk * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16 + pre_bytes;
-  auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, true> : bimamba_scan_fwd_kernel<T, N, false>;
+  const size_t pre_bytes = sizeof(T) == 2 ? (size_t)2 * G * 3 * CH * sizeof(T) : 0;
+  const size_t smem = 1024 + (size_t)2 * N * CH * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16 + pre_bytes;
+  auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, TOK, true> : bimamba_scan_fwd_kernel<T, N, TOK, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
@@ -376,6 +380,14 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
     }
   }
   CAD_REQUIRE(G >= 1 && G <= kMaxG, "cad_bimamba_scan_fwd: channels_per_cta must be in [1, %d]", kMaxG);
-  CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16>(*a, G, stream));
+  // tokens per lane: 16 (512-token chunks, 2 CTAs/SM) or 8 (256-token chunks, up to 4 CTAs/SM, 16-bit I/O only).
+  // The saved chunk states (training) are defined on 512-token chunks, so they force 16.
+  int tok = a->tokens_per_lane;
+  if (tok == 0) tok = 16;
+  CAD_REQUIRE(tok == 16 || tok == 8, "cad_bimamba_scan_fwd: tokens_per_lane must be 0, 8 or 16");
+  if (a->chunk_state || a->io_dtype == CAD_F32) tok = 16;
+  if (tok == 16) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16>(*a, G, stream)); }
+  else if (a->io_dtype == CAD_BF16) return launch_scan<__nv_bfloat16, 16, 8>(*a, G, stream);
+  else return launch_scan<__half, 16, 8>(*a, G, stream);
   return 0;
 }

@@ -14,6 +14,7 @@ from ._lib import CAD_BF16, CAD_F16, CAD_F32
 _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
+SCAN_TOKENS_PER_LANE = 0   # 0 = library default; 8 / 16 force the scan's tokens per lane (tuning knob)
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
 
@@ -285,7 +286,7 @@ def project_dt_bc(xdbl, dt_w_job, L, N):
 
 
 def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
-             channels_per_cta=0, state_only=False):
+             channels_per_cta=0, state_only=False, tokens_per_lane=None):
     """Launch the fused bidirectional scan.
     xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld)."""
     lib = _lib.load()
@@ -307,7 +308,8 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     a = _lib.ScanFwdArgs(
         _ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
-        L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only))
+        L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only),
+        SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane))
     ev = None
     if SCAN_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

@@ -144,6 +144,7 @@ typedef struct {
   int32_t io_dtype;         /* dtype of xz / delta / out / halo */
   int32_t channels_per_cta; /* 0 = library picks so that the grid is ~ a multiple of the SM count */
   int32_t state_only;       /* 1: only hlast / dtsum are produced (pass 1 of a sequence-sharded scan); out may be NULL */
+  int32_t tokens_per_lane;  /* 0 = default (16); 8 = 256-token chunks with more CTAs per SM (16-bit I/O, no chunk_state) */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
