@@ -169,48 +169,51 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
         dy[i] = masked ? 0.f : gs[phys(i)] * silu_io<T>(zz);
       }
     }
-    float ddt[kTok], dug[kTok], y[kTok];
+    float ddt[kTok], dug[kTok], y[kTok], du[kTok];
 #pragma unroll
-    for (int i = 0; i < kTok; ++i) { ddt[i] = 0.f; dug[i] = dy[i] * Dk; y[i] = Dk * u[i]; dD_acc += dy[i] * u[i]; }
+    for (int i = 0; i < kTok; ++i) {
+      ddt[i] = 0.f; dug[i] = dy[i] * Dk; y[i] = Dk * u[i]; dD_acc += dy[i] * u[i];
+      du[i] = dt[i] * u[i];
+    }
     const float dtn0 = __shfl_down_sync(0xffffffffu, dt[0], 1);
     const float dt_after = (lane == 31) ? dt_next0 : dtn0;       // dt of the token following my segment
 
     mbar_wait(sm.bar, parity);
     parity ^= 1;
     __syncwarp();
-    const unsigned char* tile_b = reinterpret_cast<const unsigned char*>(sm.tile);
+    const uint32_t tile_s = smem_u32(sm.tile);
+    const uint32_t a2_s = smem_u32(my_a2), cin_s = smem_u32(my_cin), ecar_s = smem_u32(my_ecar);
 
 #pragma unroll 1
     for (int n = 0; n < N; ++n) {
-      const float A2n = my_a2[n];
-      const float cin = my_cin[n];
-      const float ecar = my_ecar[n];
+      const float A2n = lds32(a2_s + 4 * n);
+      const float cin = lds32(cin_s + 4 * n);
+      const float ecar = lds32(ecar_s + 4 * n);
       float av[kTok], hs[kTok], beta[kTok];
       float brow[kTok];
       float hin;
       // ---------- forward recompute ------------------------------------------------------------------------
       {
         float bv[kTok];
-        const unsigned char* rowp = tile_b + n * (kChunk * 4);
+        const uint32_t rowp = tile_s + n * (kChunk * 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float4 q = *reinterpret_cast<const float4*>(rowp + poff[k]);
+          const float4 q = lds128(rowp + poff[k]);
           brow[4 * k + 0] = q.x; brow[4 * k + 1] = q.y; brow[4 * k + 2] = q.z; brow[4 * k + 3] = q.w;
         }
         float hl = (lane == 0) ? cin : 0.f;
 #pragma unroll
         for (int i = 0; i < kTok; ++i) {
           av[i] = ex2(dt[i] * A2n);
-          bv[i] = dt[i] * u[i] * brow[phys(i)];
+          bv[i] = du[i] * brow[phys(i)];
           hl = fmaf(av[i], hl, bv[i]);
         }
         float P = ex2(A2n * dsum);
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const float Pp = __shfl_up_sync(0xffffffffu, P, off);
-          const float Hp = __shfl_up_sync(0xffffffffu, hl, off);
-          if (lane >= off) { hl = fmaf(P, Hp, hl); P *= Pp; }
-        }
+        scan_step_up<1>(P, hl, lane);
+        scan_step_up<2>(P, hl, lane);
+        scan_step_up<4>(P, hl, lane);
+        scan_step_up<8>(P, hl, lane);
+        scan_step_up<16>(P, hl, lane);
         hin = __shfl_up_sync(0xffffffffu, hl, 1);
         if (lane == 0) hin = cin;
         float h = hin;
@@ -218,11 +221,11 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
         for (int i = 0; i < kTok; ++i) { h = fmaf(av[i], h, bv[i]); hs[i] = h; }
       }
       {
-        const unsigned char* rowp = tile_b + (N + n) * (kChunk * 4);
+        const uint32_t rowp = tile_s + (N + n) * (kChunk * 4);
         float cv[kTok];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float4 q = *reinterpret_cast<const float4*>(rowp + poff[k]);
+          const float4 q = lds128(rowp + poff[k]);
           cv[4 * k + 0] = q.x; cv[4 * k + 1] = q.y; cv[4 * k + 2] = q.z; cv[4 * k + 3] = q.w;
         }
 #pragma unroll
@@ -240,17 +243,16 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
       for (int i = kTok - 2; i >= 0; --i) el = fmaf(av[i + 1], el, beta[i]);
       float Q = ex2(A2n * (dsum - dt[0] + dt_after));            // prod_{i=0..15} a_{i+1}
       if (lane == 31 && last_chunk) Q = 0.f;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const float Qn = __shfl_down_sync(0xffffffffu, Q, off);
-        const float En = __shfl_down_sync(0xffffffffu, el, off);
-        if (lane + off < 32) { el = fmaf(Q, En, el); Q *= Qn; }
-      }
+      scan_step_down<1>(Q, el, lane);
+      scan_step_down<2>(Q, el, lane);
+      scan_step_down<4>(Q, el, lane);
+      scan_step_down<8>(Q, el, lane);
+      scan_step_down<16>(Q, el, lane);
       float e = __shfl_down_sync(0xffffffffu, el, 1);            // e at the first token of the next lane
       if (lane == 31) e = ecar;
       __syncwarp();
       if (lane == 0) {
-        my_ecar[n] = el;                                         // e at the first token of this chunk
+        sts32(ecar_s + 4 * n, el);                               // e at the first token of this chunk
         if (c == 0 && a.dh0 && active) a.dh0[((int64_t)job * E + ch) * N + n] = av[0] * el;
       }
       // ---------- gradients, walking the segment backwards --------------------------------------------------------
@@ -268,7 +270,7 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
         const float eB = e * brow[phys(i)];
         ddt[i] = fmaf(eB, u[i], ddt[i]);
         dug[i] = fmaf(eB, dt[i], dug[i]);
-        dBv[phys(i)] = e * dt[i] * u[i];
+        dBv[phys(i)] = e * du[i];
         dCv[phys(i)] = dy[i] * hs[i];
       }
 #pragma unroll

@@ -65,6 +65,15 @@ __device__ __forceinline__ void scan_step_up(float& P, float& H, int lane) {
       : "+f"(H), "+f"(P) : "f"(Hp), "f"(Pp), "r"(lane), "n"(OFF));
 }
 
+// mirrored step for the adjoint (suffix) scan: lanes < 32 - OFF absorb the aggregate of lane + OFF
+template <int OFF>
+__device__ __forceinline__ void scan_step_down(float& Q, float& E, int lane) {
+  const float Qn = __shfl_down_sync(0xffffffffu, Q, OFF);
+  const float En = __shfl_down_sync(0xffffffffu, E, OFF);
+  asm("{\n.reg .pred q;\nsetp.lt.s32 q, %4, %5;\n@q fma.rn.f32 %0, %1, %2, %0;\n@q mul.f32 %1, %1, %3;\n}"
+      : "+f"(E), "+f"(Q) : "f"(En), "f"(Qn), "r"(lane), "n"(32 - OFF));
+}
+
 // this lane's TOK/4 16-byte pieces inside a TMA-swizzled tile row (see scan_fwd.cu): SWIZZLE_128B stores 16-byte
 // chunk c of 128-byte line l at chunk position c ^ (l & 7); a tile row is CH/32 consecutive lines (line = 32 tokens).
 template <int TOK = kTok>

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
   T* us = wxs + 2 * MROWS * WP;                        // [KC][UP]
   T* wdts = us + KC * UP;                              // [E][DP]   (E <= 1024 guarded on the host)
   T* dts = wdts + (size_t)a.E * DP;                    // [16][UP]
+  float* cws = reinterpret_cast<float*>(dts + 16 * UP); // [2][KC][8]: conv taps (4) + bias of the slab's channels
   T* stg = xs;                                         // [8 warps][16][UP]: aliases the x slabs after the K loop
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,6 +120,12 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
       if (r < R + 2 * N) cp_async16(dst, wx + (int64_t)r * E + c0 + 8 * v);
       else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
+    if (tid < KC) {                                    // conv taps + bias of the slab's 64 channels
+      const int64_t pc = (int64_t)pset * E + c0 + tid;
+      float* cd = cws + (buf * KC + tid) * 8;
+      cp_async16(cd, a.conv_w + pc * 4);
+      cd[4] = a.conv_b[pc];
+    }
     cp_async_commit();
   };
 
@@ -155,35 +162,44 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
     const T* xb = xs + buf * KC * XP;
     const T* wb = wxs + buf * MROWS * WP;
     const int64_t c0 = (int64_t)sl * KC;
-    // ---- conv + SiLU: (channel, 8-token vector) items -> u slab ----------------------------------------------------
-    for (int i = tid; i < KC * (XT / 8); i += 256) {
-      const int ch = i / (XT / 8), v = i - ch * (XT / 8);
-      const int64_t pc = (int64_t)pset * E + c0 + ch;
-      const float4 cw = *reinterpret_cast<const float4*>(a.conv_w + pc * 4);
-      const float cb = a.conv_b[pc];
-      // three aligned vectors around my 8 tokens: x[t-8 .. t+15], t = t0 + 8v
-      const uint4* xv = reinterpret_cast<const uint4*>(xb + ch * XP + 8 * v);
-      const uint4 r0 = xv[0], r1 = xv[1], r2 = xv[2];
-      const T* e0 = reinterpret_cast<const T*>(&r0);
-      const T* e1 = reinterpret_cast<const T*>(&r1);
-      const T* e2 = reinterpret_cast<const T*>(&r2);
-      float win[14];                                   // x[t-3 .. t+10]
+    // ---- conv + SiLU: thread (chb, v) handles the 8-token vector v of channels chb, chb+16, chb+32, chb+48 -------
+    {
+      const int v = tid & 15, chb = tid >> 4;
+      const float* cwb = cws + buf * KC * 8;
 #pragma unroll
-      for (int e = 0; e < 3; ++e) win[e] = io<T>::to_f(e0[5 + e]);
+      for (int k = 0; k < KC / 16; ++k) {
+        const int ch = chb + 16 * k;
+        const float4 cw = *reinterpret_cast<const float4*>(cwb + ch * 8);
+        const float cb = cwb[ch * 8 + 4];
+        // three aligned vectors around my 8 tokens: x[t-8 .. t+15], t = t0 + 8v
+        const uint4* xv = reinterpret_cast<const uint4*>(xb + ch * XP + 8 * v);
+        const uint4 r0 = xv[0], r1 = xv[1], r2 = xv[2];
+        const T* e0 = reinterpret_cast<const T*>(&r0);
+        const T* e1 = reinterpret_cast<const T*>(&r1);
+        const T* e2 = reinterpret_cast<const T*>(&r2);
+        float win[14];                                   // x[t-3 .. t+10]
 #pragma unroll
-      for (int e = 0; e < 8; ++e) win[3 + e] = io<T>::to_f(e1[e]);
+        for (int e = 0; e < 3; ++e) win[e] = io<T>::to_f(e0[5 + e]);
 #pragma unroll
-      for (int e = 0; e < 3; ++e) win[11 + e] = io<T>::to_f(e2[e]);
-      uint4 outv;
-      T* o = reinterpret_cast<T*>(&outv);
+        for (int e = 0; e < 8; ++e) win[3 + e] = io<T>::to_f(e1[e]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float c;
-        if (!rev) c = cb + cw.x * win[e] + cw.y * win[e + 1] + cw.z * win[e + 2] + cw.w * win[e + 3];
-        else      c = cb + cw.w * win[e + 3] + cw.z * win[e + 4] + cw.y * win[e + 5] + cw.x * win[e + 6];
-        o[e] = io<T>::from_f(silu_io<T>(c));
+        for (int e = 0; e < 3; ++e) win[11 + e] = io<T>::to_f(e2[e]);
+        uint4 outv;
+        uint32_t* o = reinterpret_cast<uint32_t*>(&outv);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          float c0v, c1v;
+          if (!rev) {
+            c0v = cb + cw.x * win[e] + cw.y * win[e + 1] + cw.z * win[e + 2] + cw.w * win[e + 3];
+            c1v = cb + cw.x * win[e + 1] + cw.y * win[e + 2] + cw.z * win[e + 3] + cw.w * win[e + 4];
+          } else {
+            c0v = cb + cw.w * win[e + 3] + cw.z * win[e + 4] + cw.y * win[e + 5] + cw.x * win[e + 6];
+            c1v = cb + cw.w * win[e + 4] + cw.z * win[e + 5] + cw.y * win[e + 6] + cw.x * win[e + 7];
+          }
+          o[e >> 1] = pack2<T>(silu_io<T>(c0v), silu_io<T>(c1v));
+        }
+        *reinterpret_cast<uint4*>(us + ch * UP + 8 * v) = outv;
       }
-      *reinterpret_cast<uint4*>(us + ch * UP + 8 * v) = outv;
     }
     __syncthreads();
     // ---- x_proj MMA: acc[m][j] += W_x[16m.., slab] . u[slab, 16 warp + 8j ..] -----------------------------------
@@ -277,7 +293,8 @@ extern "C" int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream_) {
               a->ldbc % 2 == 0, "cad_conv_xproj_fwd: alignment");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   static_assert(2 * KC * XP >= 8 * 16 * UP, "output staging must fit in the x slabs it aliases");
-  const size_t smem = sizeof(uint16_t) * ((size_t)2 * KC * XP + 2 * MROWS * WP + KC * UP + (size_t)a->E * DP + 16 * UP);
+  const size_t smem = sizeof(uint16_t) * ((size_t)2 * KC * XP + 2 * MROWS * WP + KC * UP + (size_t)a->E * DP + 16 * UP) +
+                      sizeof(float) * 2 * KC * 8;
   dim3 grid((unsigned)((a->L + XT - 1) / XT), (unsigned)a->njobs);
   cudaError_t e;
   if (a->io_dtype == CAD_BF16) {
