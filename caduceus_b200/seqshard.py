@@ -53,42 +53,68 @@ def sequence_parallel(group=None):
 
 
 def _all_gather(t, ctx):
-    out = [torch.empty_like(t) for _ in range(ctx.world)]
-    dist.all_gather(out, t.contiguous(), group=ctx.group)
-    return torch.stack(out)                                    # (world, ...)
+    """(world, *t.shape) — one collective, one output buffer."""
+    t = t.contiguous()
+    out = torch.empty((ctx.world,) + tuple(t.shape), device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out.view(ctx.world * t.shape[0], *t.shape[1:]) if t.dim() > 0 else out, t,
+                                group=ctx.group)
+    return out
+
+
+_HALO_INDEX = {}
+
+
+def _halo_index(seq_l, rev_l, rank, world, device):
+    """Per job: which (rank, edge, sequence) supplies its halo, whether it is reversed, and whether it exists."""
+    key = (seq_l, rev_l, rank, world, str(device))
+    hit = _HALO_INDEX.get(key)
+    if hit is None:
+        src_rank = [rank + 1 if r else rank - 1 for r in rev_l]
+        valid = [0 <= q < world for q in src_rank]
+        src_rank = [q if ok else rank for q, ok in zip(src_rank, valid)]
+        edge = [0 if r else 1 for r in rev_l]                      # reversed jobs take the successor's FIRST three
+        mk = lambda v, dt: torch.tensor(v, dtype=dt, device=device)     # noqa: E731
+        hit = (mk(src_rank, torch.long), mk(edge, torch.long), mk(list(seq_l), torch.long),
+               mk(list(rev_l), torch.bool)[:, None, None], mk(valid, torch.bool)[:, None, None])
+        _HALO_INDEX[key] = hit
+    return hit
 
 
 def gather_halo(x_rows, L, seq_of_job, rev_of_job, ctx):
     """x_rows (nseq, E, >=L): the conv input rows of this shard.  Returns halo (njobs, E, 3) = the 3 samples
     logically preceding the shard for each job (zeros at the ends of the full sequence), in logical order."""
     assert L >= 3, "sequence shards must hold at least 3 tokens"
-    edges = torch.stack([x_rows[..., 0:3], x_rows[..., L - 3:L]])              # (2, nseq, E, 3): first3, last3
-    allv = _all_gather(edges, ctx)                                              # (world, 2, nseq, E, 3)
-    zero = torch.zeros_like(edges[0, 0])
-    halos = []
     from . import functional as CF
     host = CF.JOB_HOST.get(seq_of_job.data_ptr())
-    seq_l, rev_l = (host[0], host[2]) if host is not None else (seq_of_job.tolist(), rev_of_job.tolist())
-    for s, r in zip(seq_l, rev_l):
-        if not r:      # left-to-right: predecessor rank's LAST three samples, already in logical order
-            halos.append(allv[ctx.rank - 1, 1, s] if ctx.rank > 0 else zero)
-        else:          # right-to-left: successor rank's FIRST three, logical order = physical order reversed
-            halos.append(allv[ctx.rank + 1, 0, s].flip(-1) if ctx.rank + 1 < ctx.world else zero)
-    return torch.stack(halos).contiguous()
+    seq_l, rev_l = (host[0], host[2]) if host is not None else (tuple(seq_of_job.tolist()), tuple(rev_of_job.tolist()))
+    edges = torch.stack([x_rows[..., 0:3], x_rows[..., L - 3:L]])              # (2, nseq, E, 3): first3, last3
+    allv = _all_gather(edges, ctx)                                              # (world, 2, nseq, E, 3)
+    src_rank, edge, seq_i, is_rev, valid = _halo_index(seq_l, rev_l, ctx.rank, ctx.world, x_rows.device)
+    h = allv[src_rank, edge, seq_i]                                             # (njobs, E, 3)
+    # left-to-right jobs: predecessor's LAST three, already in logical order; right-to-left: successor's FIRST three,
+    # logical order = physical order reversed
+    h = torch.where(is_rev, h.flip(-1), h)
+    return torch.where(valid, h, torch.zeros_like(h)).contiguous()
 
 
 def compose_carry(h_all, dtsum_all, A2_job, rev_of_job, rank):
     """h_all (world, njobs, E, N) zero-carry end states, dtsum_all (world, njobs, E), A2_job (njobs, E, N).
-    Carry-in of `rank`:  walk the logical predecessors applying  h <- exp2(A2 * sum dt) * h + H."""
+    Carry-in of `rank`:  h0 = sum over logical predecessors j of  exp2(A2 * sum(dt over the ranks between j and rank)) * H_j
+    (the affine composition h <- exp2(A2 * sum dt_j) * h + H_j unrolled), vectorised over the ranks."""
     world = h_all.shape[0]
-    fwd = torch.zeros_like(h_all[0])
-    for j in range(0, rank):
-        fwd = torch.exp2(A2_job * dtsum_all[j][..., None]) * fwd + h_all[j]
-    bwd = torch.zeros_like(h_all[0])
-    for j in range(world - 1, rank, -1):
-        bwd = torch.exp2(A2_job * dtsum_all[j][..., None]) * bwd + h_all[j]
-    rev = rev_of_job.to(torch.bool)[:, None, None]
-    return torch.where(rev, bwd, fwd).contiguous()
+    idx = torch.arange(world, device=h_all.device)
+    csum = torch.cumsum(dtsum_all, dim=0)                                        # inclusive over ranks
+    total = csum[-1]
+    # left-to-right jobs: predecessors j < rank, decay over ranks j+1 .. rank-1  ->  S(rank-1) - S(j)
+    upto = csum[rank - 1] if rank > 0 else torch.zeros_like(total)
+    between_f = (upto[None] - csum).clamp_min(0.0)
+    w_f = torch.exp2(A2_job[None] * between_f[..., None]) * (idx < rank)[:, None, None, None]
+    # right-to-left jobs: predecessors j > rank, decay over ranks rank+1 .. j-1  ->  S(j-1) - S(rank)
+    csum_prev = csum - dtsum_all
+    between_r = (csum_prev - csum[rank][None]).clamp_min(0.0)
+    w_r = torch.exp2(A2_job[None] * between_r[..., None]) * (idx > rank)[:, None, None, None]
+    rev = rev_of_job.to(torch.bool)[None, :, None, None]
+    return (torch.where(rev, w_r, w_f) * h_all).sum(0).contiguous()
 
 
 def gather_carry(hlast, dtsum, A2, pset_of_job, rev_of_job, ctx):
