@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: MLM step = forward + loss + backward + AdamW under bf16 autocast (BASELINE configs[3] on 1 GPU)")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the forward from a CUDA graph (single-GPU / replica forward only; helps short sequences)")
     ap.add_argument("--scan-tok", type=int, default=0, choices=[0, 8, 16], help="tokens per lane of the scan kernel (tuning)")
     ap.add_argument("--shard", default="none", choices=["none", "seq"],
                     help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
@@ -275,14 +277,35 @@ def run_b200(a):
         step_device(i)
         step_e2e(i)
 
+    graphed = False
+    if a.graph and not train and not shard_seq:
+        from caduceus_b200.graphs import GraphedForward
+        CF.LAUNCHES = 0
+        step_device(0)
+        launches_per_step = CF.LAUNCHES
+        gfwd = GraphedForward(model, dev_ids[0])
+        graphed = True
+
+        def step_device(i):        # noqa: F811
+            return gfwd(dev_ids[i % nbuf])
+
+        def step_e2e(i):           # noqa: F811
+            logits = gfwd(host_ids[i % nbuf])
+            host_out.copy_(logits, non_blocking=True)
+            return logits
+
+        for i in range(2):
+            step_device(i)
+            step_e2e(i)
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     CF.LAUNCHES = 0
-    CF.SCAN_EVENTS = []                      # (start, end) CUDA events around every fused-scan launch
+    CF.SCAN_EVENTS = None if graphed else []     # (start, end) CUDA events around every fused-scan launch
     ms_dev = timed(step_device, a.steps)
-    launches = CF.LAUNCHES
-    scan_events, CF.SCAN_EVENTS = CF.SCAN_EVENTS, None
+    launches = launches_per_step * a.steps if graphed else CF.LAUNCHES     # a replayed graph re-runs the captured launches
+    scan_events, CF.SCAN_EVENTS = (CF.SCAN_EVENTS or []), None
     ms_e2e = timed(step_e2e, a.steps)
     if sampler:
         sampler.stop_flag.set()
@@ -344,7 +367,8 @@ def run_b200(a):
             "dtype": "bf16", "data": "synthetic", "mode": a.mode,
             "config": {"workload": workload_name(a), "parallelism": (f"sp{world} (one sequence sharded on the sequence axis, 2 tiny all_gathers per layer)"
                                        if shard_seq else f"dp{world} (independent sequences per GPU)"),
-                       "l2": "per-step working set > 1 GB >> 126 MB L2; 4 rotating input batches"},
+                       "l2": "per-step working set > 1 GB >> 126 MB L2; 4 rotating input batches",
+                       "launch": "CUDA graph replay" if graphed else "eager"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": a.batch * a.seqlen * 8 * world,
                     "d2h_bytes_per_step": (4 if train else a.batch * a.seqlen * cfg.vocab_size * 4) * world},
