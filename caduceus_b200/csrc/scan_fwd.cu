@@ -1,4 +1,4 @@
-// Fused bidirectional selective-scan forward for sm_100a (v2: TMA-staged tile, 2 CTAs/SM).
+// Fused bidirectional selective-scan forward for sm_100a (TMA-staged B/C tile, cp.async-staged x/dt/z, 2 CTAs/SM).
 //
 // One launch covers every (sequence, direction) "job" of a BiMamba call — forward and reverse directions of
 // ref:caduceus/modeling_caduceus.py:128-137 and both strands of ref:caduceus/modeling_rcps.py:85-99 — with the
@@ -10,8 +10,10 @@
 //
 // Work decomposition (B200: 148 SMs; the scan is MUFU/issue-bound, not HBM-bound — SURVEY.md §8d):
 //   CTA  = one job x G <= 7 consecutive channels, one WARP PER CHANNEL, walking the sequence in logical-time
-//          chunks of 512 tokens; 2 CTAs are resident per SM (<= 146 registers, 66 KB smem), so Caduceus-PS
-//          (4 jobs x 74 CTAs) is a single wave of 296 CTAs and each SM holds 14 warps.
+//          chunks of 512 tokens; 2 CTAs are resident per SM (128 registers, 109 KB smem), so Caduceus-PS
+//          (4 jobs x 74 CTAs) is a single wave of 296 CTAs and each SM holds 14 warps — which is ALL the channel
+//          parallelism there is at batch 1 (2048 channel-jobs / 148 SMs): more warps per SM would need more
+//          than one warp per channel (tried, no gain: DESIGN.md §9).
 //   lane = 16 consecutive tokens of the chunk.  Each lane runs the recurrence over its 16 tokens from a zero
 //          state, the 32 segment aggregates (prod a, h_end) are combined with a 5-step warp-shuffle scan, and
 //          the lane re-runs its 16 FMAs from the true incoming state.  exp2 is evaluated ONCE per
@@ -20,8 +22,11 @@
 //          (cp.async.bulk.tensor.3d, SWIZZLE_128B) per chunk into a bank-conflict-free layout; tokens beyond
 //          the sequence end are zero-filled by the TMA unit.  The request for chunk c+1 is issued before the
 //          gate/store epilogue of chunk c, so its latency hides behind the epilogue and the next prologue.
-//   profile of v1 that motivated this layout: profiles/r1_v1_scan_ncu_summary.txt (20.8 warp-instructions per
-//   element, 7.6 of them integer/select overhead of the cp.async+widen tile path; 43 % issue utilisation).
+//          The lane's own x / dt_raw / z segments of chunk c+1 are staged by cp.async during chunk c (16-bit I/O).
+//   template knobs: TOK tokens per lane (16; 8 = 256-token chunks for many-CTA workloads), STATE_ONLY (end state and
+//   sum(dt) only, no output), REV/TAIL specialisations (reversed jobs; the one chunk that straddles the sequence end).
+//   profiles: profiles/r1_v1_scan_ncu_summary.txt (v1: 20.8 warp-instructions per element, 43 % issue utilisation)
+//   -> profiles/r1_v3_scan_and_bwd_ncu_summary.txt (11.4 instructions per element, MUFU pipe 53 %, issue 57 %).
 #include "scan_common.cuh"
 
 namespace cad {

@@ -217,7 +217,8 @@ typedef struct {
 } cad_conv_xproj_args;
 int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
 
-/* v1 helper: u = silu(conv(x)) materialised per job for the x_proj GEMM  (njobs, E, ldu). */
+/* unfused helper (fp32 I/O and the training path, which needs u for the x_proj weight gradient):
+ * u = silu(conv(x)) materialised per job as the operand of a cuBLAS x_proj GEMM  (njobs, E, ldu). */
 typedef struct {
   const void* xz; void* u;
   const float* conv_w; const float* conv_b;
