@@ -56,16 +56,27 @@ class BiMambaWrapper(nn.Module):
             raise NotImplementedError(f"`{bidirectional_strategy}` strategy for bi-directionality is not implemented!")
         self.bidirectional = bidirectional
         self.bidirectional_strategy = bidirectional_strategy
+        self.bidirectional_weight_tie = bool(bidirectional and bidirectional_weight_tie)
         self.mamba_fwd = Mamba(d_model=d_model, **mamba_kwargs)
         self.mamba_rev = None
         if bidirectional:
             self.mamba_rev = Mamba(d_model=d_model, **mamba_kwargs)
-            if bidirectional_weight_tie:
-                # the two projections hold most of the parameters; conv/x_proj/dt_proj/A/D stay per direction
-                for proj in ("in_proj", "out_proj"):
-                    src, dst = getattr(self.mamba_fwd, proj), getattr(self.mamba_rev, proj)
-                    dst.weight = src.weight
-                    dst.bias = src.bias
+            self.tie_projections()
+
+    def tie_projections(self):
+        """mamba_rev shares in_proj / out_proj with mamba_fwd (ref:caduceus/modeling_caduceus.py:114-118): the two
+        projections hold most of the parameters; conv / x_proj / dt_proj / A / D stay per direction."""
+        if self.bidirectional_weight_tie:
+            tied = {}
+            for proj in ("in_proj", "out_proj"):
+                src, dst = getattr(self.mamba_fwd, proj), getattr(self.mamba_rev, proj)
+                dst.weight = src.weight
+                dst.bias = src.bias
+                tied[f"mamba_rev.{proj}.weight"] = f"mamba_fwd.{proj}.weight"
+                if src.bias is not None:
+                    tied[f"mamba_rev.{proj}.bias"] = f"mamba_fwd.{proj}.bias"
+            # transformers >= 5 walks submodules for this attribute when it serialises shared tensors
+            self._tied_weights_keys = tied
 
     def forward(self, hidden_states, inference_params=None):
         """hidden_states (B, L, D) -> (B, L, D)."""
@@ -167,20 +178,46 @@ class CaduceusPreTrainedModel(PreTrainedModel):
     supports_gradient_checkpointing = False
     _no_split_modules = ["BiMambaWrapper"]
 
+    def get_expanded_tied_weights_keys(self, all_submodels: bool = False) -> dict:
+        """{duplicate parameter name: canonical name} for every parameter this model shares: the BiMamba projection
+        ties (structural, independent of `config.tie_word_embeddings`) plus the head/embedding tie.  transformers >= 5
+        needs the map to save / reload shared tensors; 4.x simply dropped duplicates with a warning."""
+        try:
+            mapping = dict(super().get_expanded_tied_weights_keys(all_submodels=all_submodels))
+        except (AttributeError, TypeError):        # transformers 4.x has no such hook
+            mapping = {}
+        seen = {}
+        for name, p in self.named_parameters(remove_duplicate=False):
+            if id(p) in seen:
+                mapping.setdefault(name, seen[id(p)])
+            else:
+                seen[id(p)] = name
+        return mapping
+
+    def _retie_structural(self):
+        for m in self.modules():
+            if isinstance(m, BiMambaWrapper):
+                m.tie_projections()
+
     def _init_weights(self, module, initializer_range=0.02, **kwargs):
         """Mamba's GPT-2-style init (ref:caduceus/modeling_caduceus.py:304-341): zero Linear biases (except
         `_no_reinit` ones such as dt_proj.bias), N(0, range) embeddings, out_proj rescaled by
         1/sqrt(n_residuals_per_layer * n_layer)."""
         cfg = self.config.initializer_cfg or {}
+
+        def loaded(p):      # transformers >= 5 flags parameters it has just read from a checkpoint: leave those alone
+            return getattr(p, "_is_hf_initialized", False)
+
         if isinstance(module, nn.Linear):
-            if module.bias is not None and not getattr(module.bias, "_no_reinit", False):
+            if module.bias is not None and not getattr(module.bias, "_no_reinit", False) and not loaded(module.bias):
                 nn.init.zeros_(module.bias)
         elif isinstance(module, nn.Embedding):
-            nn.init.normal_(module.weight, std=cfg.get("initializer_range", initializer_range))
+            if not loaded(module.weight):
+                nn.init.normal_(module.weight, std=cfg.get("initializer_range", initializer_range))
         if cfg.get("rescale_prenorm_residual", True):
             scale = math.sqrt(cfg.get("n_residuals_per_layer", 1) * self.config.n_layer)
             for name, p in module.named_parameters():
-                if name in ("out_proj.weight", "fc2.weight"):
+                if name in ("out_proj.weight", "fc2.weight") and not loaded(p):
                     # re-draw before scaling so that repeated calls do not shrink the weight repeatedly
                     nn.init.kaiming_uniform_(p, a=math.sqrt(5))
                     with torch.no_grad():
@@ -196,6 +233,9 @@ def _return_dict(config, return_dict):
 class Caduceus(CaduceusPreTrainedModel):
     """Backbone: embeddings -> n_layer blocks -> final norm.  ref:caduceus/modeling_caduceus.py:344-389."""
 
+    def tie_weights(self, **kwargs):
+        self._retie_structural()
+
     def __init__(self, config: CaduceusConfig, device=None, dtype=None, **kwargs):
         super().__init__(config)
         if config.rcps and config.complement_map is None:
@@ -210,6 +250,9 @@ class Caduceus(CaduceusPreTrainedModel):
                 config.complement_map[i] = i
         self.config = config
         self.backbone = CaduceusMixerModel(config, device=device, dtype=dtype, **kwargs)
+        # the reference leaves the bare backbone un-"post_init"-ed (it is initialised through the head models);
+        # transformers >= 5 needs the bookkeeping post_init() sets up to load it standalone via AutoModel
+        self.post_init()
 
     def forward(self, input_ids: torch.LongTensor = None, inputs_embeds: Optional[torch.FloatTensor] = None,
                 output_hidden_states: Optional[bool] = None, return_dict: Optional[bool] = None,
@@ -239,6 +282,12 @@ class CaduceusForMaskedLM(CaduceusPreTrainedModel):
                                       true_dim=config.d_model, dtype=dtype)
         else:
             self.lm_head = nn.Linear(config.d_model, self.config.vocab_size, bias=False, device=device, dtype=dtype)
+        # head <-> table tie, declared for transformers >= 5 (PS always; Ph when config.tie_word_embeddings)
+        emb = "caduceus.backbone.embeddings.word_embeddings."
+        if config.rcps:
+            self._tied_weights_keys = {"lm_head.lm_head.weight": emb + "embedding.weight"}
+        elif getattr(config, "tie_word_embeddings", True):
+            self._tied_weights_keys = {"lm_head.weight": emb + "weight"}
         self.post_init()
 
     def get_input_embeddings(self):
@@ -260,6 +309,7 @@ class CaduceusForMaskedLM(CaduceusPreTrainedModel):
     def tie_weights(self, **kwargs):
         """PS always shares the table with the head (ref:caduceus/modeling_caduceus.py:434-439); Ph follows
         `config.tie_word_embeddings` (True under the reference's transformers pin)."""
+        self._retie_structural()
         if self.config.rcps:
             self.lm_head.set_weight(self.get_input_embeddings().weight)
         elif getattr(self.config, "tie_word_embeddings", True):
@@ -315,6 +365,9 @@ class CaduceusForSequenceClassification(CaduceusPreTrainedModel):
         self.conjoin_eval = conjoin_eval
         self.post_init()
         self.init_scorer()
+
+    def tie_weights(self, **kwargs):
+        self._retie_structural()
 
     def init_scorer(self, initializer_range=0.02):
         cfg = self.config.initializer_cfg or {}

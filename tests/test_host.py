@@ -128,3 +128,27 @@ def test_job_tables():
     assert rev.tolist() == [0, 1, 1, 0] * 2          # strand 1: mamba_fwd runs right-to-left, mamba_rev left-to-right
     seq_u, _, _ = CF.job_tables(1, 1, 2, True, "cpu")
     assert seq_u.tolist() == [0, 1]
+
+
+@pytest.mark.parametrize("rcps", [False, True])
+def test_hf_save_pretrained_roundtrip(tmp_path, rcps):
+    """HF save_pretrained / from_pretrained keeps every tensor and every tie (head<->table, mamba_rev<->mamba_fwd
+    projections) under the installed transformers; the bare backbone loads through AutoModel from the same files."""
+    from transformers import AutoModel, AutoModelForMaskedLM
+    cmap = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 6, 7: 10, 8: 9, 9: 8, 10: 7, 11: 11}
+    cfg = caduceus.CaduceusConfig(d_model=64, n_layer=2, vocab_size=12, ssm_cfg={"d_state": 16}, rcps=rcps,
+                                  complement_map=dict(cmap) if rcps else None)
+    m = caduceus.CaduceusForMaskedLM(cfg)
+    m.save_pretrained(tmp_path)
+    m2 = AutoModelForMaskedLM.from_pretrained(tmp_path)
+    sd1, sd2 = m.state_dict(), m2.state_dict()
+    assert list(sd1) == list(sd2) and all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    mixer = m2.caduceus.backbone.layers[0].mixer
+    mixer = mixer.submodule if rcps else mixer
+    assert mixer.mamba_rev.in_proj.weight is mixer.mamba_fwd.in_proj.weight
+    assert mixer.mamba_rev.out_proj.weight is mixer.mamba_fwd.out_proj.weight
+    assert m2.lm_head.weight.data_ptr() == m2.get_input_embeddings().weight.data_ptr()
+    backbone = AutoModel.from_pretrained(tmp_path)
+    assert isinstance(backbone, caduceus.Caduceus)
+    bsd = backbone.state_dict()
+    assert all(torch.equal(bsd[k], sd1["caduceus." + k]) for k in bsd)
