@@ -234,9 +234,20 @@ def run_b200(a):
     def train_step(ids):
         inp, tgt = mlm(ids)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = model(inp, labels=tgt).loss
+            if shard_seq:
+                # every rank: its shard's logits -> CE summed over its masked tokens / the GLOBAL count; the backward
+                # gathers the adjoint carries (seqshard.py), then the partial parameter gradients are summed
+                logits = model(inp).logits
+                cnt = (tgt != 4).sum()
+                dist.all_reduce(cnt)
+                loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]).float(), tgt.reshape(-1),
+                                                         ignore_index=4, reduction="sum") / cnt
+            else:
+                loss = model(inp, labels=tgt).loss
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if shard_seq:
+            seqshard.all_reduce_grads(_model)
         opt.step()
         return loss
 

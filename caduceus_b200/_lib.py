@@ -63,13 +63,21 @@ class ScanFixupArgs(C.Structure):
                 ("cutoff_log2", _f32)]
 
 
+class ScanAdjointArgs(C.Structure):
+    _fields_ = [("xz", _p), ("delta", _p), ("bc", _p), ("dout", _p), ("dt_b", _p), ("A2", _p),
+                ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("dh", _p),
+                ("L", _i64), ("E", _i64), ("N", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
+                ("cutoff_log2", _f32)]
+
+
 class ScanBwdArgs(C.Structure):
     _fields_ = [("xz", _p), ("delta", _p), ("bc", _p), ("dout", _p),
                 ("conv_w", _p), ("conv_b", _p), ("dt_b", _p), ("A2", _p), ("Dskip", _p),
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p),
                 ("halo", _p), ("h0", _p), ("chunk_state", _p),
                 ("dz", _p), ("du", _p), ("ddelta", _p), ("dbc", _p),
-                ("ddt_b", _p), ("dA2", _p), ("dDskip", _p), ("dh0", _p),
+                ("ddt_b", _p), ("dA2", _p), ("dDskip", _p), ("dh0", _p), ("dhlast", _p),
                 ("L", _i64), ("E", _i64), ("N", _i64), ("K", _i64),
                 ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64), ("lddz", _i64), ("lddu", _i64),
                 ("lddd", _i64),
@@ -81,6 +89,13 @@ class ConvBwdArgs(C.Structure):
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
                 ("L", _i64), ("E", _i64), ("ldxz", _i64), ("lddu", _i64), ("lddx", _i64),
                 ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32)]
+
+
+class Hg38BatchArgs(C.Structure):
+    _fields_ = [("raw", _p), ("rc_flags", _p), ("char_to_id", _p),
+                ("masked", _p), ("replaced", _p), ("random_sel", _p), ("random_words", _p),
+                ("data", _p), ("target", _p), ("B", _i64), ("L", _i64),
+                ("n_id", _i64), ("pad_id", _i64), ("mask_id", _i64)]
 
 
 class ConvXprojArgs(C.Structure):
@@ -115,6 +130,8 @@ SYMBOLS = {
     "cad_bimamba_scan_fixup": (C.c_int, [C.POINTER(ScanFixupArgs), _p]),
     "cad_conv_silu_bwd": (C.c_int, [C.POINTER(ConvBwdArgs), _p]),
     "cad_conv_xproj_fwd": (C.c_int, [C.POINTER(ConvXprojArgs), _p]),
+    "cad_bimamba_scan_adjoint": (C.c_int, [C.POINTER(ScanAdjointArgs), _p]),
+    "cad_hg38_batch_fwd": (C.c_int, [C.POINTER(Hg38BatchArgs), _p]),
     "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),
 }
 

@@ -67,7 +67,8 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
   float* my_dA2 = sm.dA2acc + warp * N;
   if (lane < N) {
     my_a2[lane] = a.A2[pc * N + lane];
-    my_ecar[lane] = 0.f;
+    // adjoint carry-in: d loss / d (state after the last token) when a later shard consumes it (sequence sharding)
+    my_ecar[lane] = (a.dhlast && active) ? a.dhlast[((int64_t)job * E + chc) * N + lane] : 0.f;
     my_dA2[lane] = 0.f;
   }
   float hal[3] = {0.f, 0.f, 0.f};
@@ -106,7 +107,9 @@ __device__ __forceinline__ void scan_bwd_job(const cad_scan_bwd_args& a, const C
     const int64_t pcidx = REV ? nchunks - 1 - c : c;
     const int64_t tseg = pcidx * kChunk + (int64_t)seg * kTok;
     const bool seg_in = tseg < L;
-    const bool last_chunk = (c == nchunks - 1);
+    // nothing follows the last chunk unless an adjoint carry-in is given: then it acts as a virtual next token with
+    // dt = 0 (a = 1) — masked tail tokens already pass e through unchanged (dt = 0, beta = 0)
+    const bool last_chunk = (c == nchunks - 1) && a.dhlast == nullptr;
 
     // ---- state at the start of this chunk ---------------------------------------------------------------
     if (lane < N) {

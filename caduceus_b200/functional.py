@@ -339,9 +339,53 @@ def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, chann
     return out
 
 
+def scan_adjoint(xz, delta, bc, dout, packed, jobs, L, cutoff_log2=-40.0, channels_per_cta=0):
+    """Dh (njobs, E, N): gradient w.r.t. the shard's carry-in state from the shard's own tokens (zero adjoint
+    carry-in) — the quantity the ranks all_gather in a sequence-sharded backward.  See csrc/scan_adjoint.cu."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    _, _, dt_b, A2, _ = packed
+    nseq, twoE, ldxz = xz.shape
+    E = twoE // 2
+    njobs, twoN, ldbc = bc.shape
+    dout = dout if dout.stride(-1) == 1 and dout.stride(1) % 16 == 0 else dout.contiguous()
+    dh = torch.zeros(njobs, E, twoN // 2, device=xz.device, dtype=torch.float32)
+    if L == 0:
+        return dh
+    a = _lib.ScanAdjointArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(dout), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
+                             _ptr(rev), _ptr(dh), L, E, twoN // 2, ldxz, delta.stride(1), ldbc, dout.stride(1),
+                             nseq, njobs, _dt(xz), channels_per_cta, float(cutoff_log2))
+    _lib.check(lib.cad_bimamba_scan_adjoint(C.byref(a), _stream()), "cad_bimamba_scan_adjoint")
+    _launched()
+    return dh
+
+
+def conv_halo_grad(xz, du_total, halo, conv_w4, conv_b, jobs, L):
+    """Gradient w.r.t. the conv halo (njobs, E, 3), i.e. w.r.t. the 3 `x` samples of the logically PREVIOUS shard
+    that this shard's first three conv outputs read.  Tiny (3 tokens per job and channel), so plain torch:
+        c[tau] = b + sum_k w[k] xin[tau+k],  xin = [halo, x_logical[0:3]],  dc = du * silu'(c),  tau = 0..2
+        dhalo[j] = sum_{tau <= j} w[j - tau] * dc[tau]"""
+    seq, pset, rev = jobs
+    E = xz.shape[1] // 2
+    seq_l, pset_l = seq.long(), pset.long()
+    is_rev = rev.to(torch.bool)[:, None, None]
+    xs = xz[:, :E]
+    x_first = xs[..., 0:3].index_select(0, seq_l)
+    x_last = xs[..., L - 3:L].index_select(0, seq_l).flip(-1)
+    xin = torch.cat([halo.float(), torch.where(is_rev, x_last, x_first).float()], dim=-1)       # logical -3 .. 2
+    du3 = torch.where(is_rev, du_total[..., L - 3:L].flip(-1), du_total[..., 0:3]).float()       # logical 0 .. 2
+    w = conv_w4.index_select(0, pset_l).float()                                                    # (njobs, E, 4)
+    b = conv_b.index_select(0, pset_l).float()[..., None]
+    c = b + sum(w[..., k:k + 1] * xin[..., k:k + 3] for k in range(4))                             # (njobs, E, 3)
+    sg = torch.sigmoid(c)
+    dc = du3 * sg * (1.0 + c * (1.0 - sg))
+    return torch.stack([sum(w[..., j - t] * dc[..., t] for t in range(j + 1)) for j in range(3)], dim=-1)
+
+
 def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None, want_dh0=False,
-             channels_per_cta=0):
-    """Backward of scan_fwd: returns dz, du (scan path), ddelta (io dtype), dbc (fp32), ddt_b, dA2, dD, dh0."""
+             channels_per_cta=0, dhlast=None):
+    """Backward of scan_fwd: returns dz, du (scan path), ddelta (io dtype), dbc (fp32), ddt_b, dA2, dD, dh0.
+    `dhlast` (njobs, E, N): gradient w.r.t. the end state, i.e. the adjoint entering from the next shard."""
     lib = _lib.load()
     seq, pset, rev = jobs
     conv_w4, conv_b, dt_b, A2, Dk = packed
@@ -359,10 +403,12 @@ def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None
     dA2 = torch.zeros(P, E, N, device=dev, dtype=torch.float32)
     dD = torch.zeros(P, E, device=dev, dtype=torch.float32)
     dh0 = torch.empty(njobs, E, N, device=dev, dtype=torch.float32) if want_dh0 else None
+    dhlast = None if dhlast is None else dhlast.float().contiguous()
     a = _lib.ScanBwdArgs(
         _ptr(xz), _ptr(delta), _ptr(bc), _ptr(dout), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(cstate),
         _ptr(dz), _ptr(du), _ptr(ddelta), _ptr(dbc), _ptr(ddt_b), _ptr(dA2), _ptr(dD), _ptr(dh0),
+        _ptr(dhlast),
         L, E, N, 4, ldxz, delta.stride(1), ldbc, dout.stride(1), ldxz, ldxz, ldxz,
         nseq, njobs, P, _dt(xz), channels_per_cta)
     _lib.check(lib.cad_bimamba_scan_bwd(C.byref(a), _stream()), "cad_bimamba_scan_bwd")
@@ -394,29 +440,47 @@ class _BiMambaCoreFn(torch.autograd.Function):
     (the backward of upstream's MambaInnerFn, SURVEY.md row A16, minus the in/out projections which stay in autograd)."""
 
     @staticmethod
-    def forward(ctx, xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, jobs, L):
+    def forward(ctx, xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, jobs, L, shard=None):
         packed = (conv_w4, conv_b, dt_b, A2, Dk)
         N = A2.shape[-1]
+        E = xz.shape[1] // 2
         pset_l = jobs[1].long()
-        u = conv_silu(xz, conv_w4, conv_b, jobs, L)
+        sharded = shard is not None and shard.world > 1
+        halo = h0 = dt_all = None
+        if sharded:
+            from . import seqshard
+            halo = seqshard.gather_halo(xz[:, :E, :], L, jobs[0], jobs[2], shard).to(xz.dtype)
+        u = conv_silu(xz, conv_w4, conv_b, jobs, L, halo=halo)
         xdbl = torch.bmm(w_x.index_select(0, pset_l), u)
         del u
         delta, bc = project_dt_bc(xdbl, w_dt.index_select(0, pset_l), L, N)
-        yg, _, _, cstate = scan_fwd(xz, delta, bc, packed, jobs, L, want_chunk_state=True)
-        ctx.save_for_backward(xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, delta, bc, cstate, xdbl)
-        ctx.jobs, ctx.L = jobs, L
+        if sharded:
+            # TRUE carry for training: zero-carry state pass -> one all_gather -> full scan from h0, so that the saved
+            # chunk states (and hence the backward's recomputation) are those of the unsharded sequence
+            _, hl, ds, _ = scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, state_only=True)
+            h0, dt_all = seqshard.gather_carry(hl, ds, A2, jobs[1], jobs[2], shard, return_dtsum=True)
+        yg, _, _, cstate = scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, h0=h0, want_chunk_state=True)
+        ctx.save_for_backward(xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, delta, bc, cstate, xdbl, halo, h0, dt_all)
+        ctx.jobs, ctx.L, ctx.shard = jobs, L, (shard if sharded else None)
         return yg
 
     @staticmethod
     def backward(ctx, dyg):
-        xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, delta, bc, cstate, xdbl = ctx.saved_tensors
-        jobs, L = ctx.jobs, ctx.L
+        xz, w_x, w_dt, conv_w4, conv_b, dt_b, A2, Dk, delta, bc, cstate, xdbl, halo, h0, dt_all = ctx.saved_tensors
+        jobs, L, shard = ctx.jobs, ctx.L, ctx.shard
         packed = (conv_w4, conv_b, dt_b, A2, Dk)
         P, _, N = A2.shape
         R = w_dt.shape[-1]
         pset_l, seq_l = jobs[1].long(), jobs[0].long()
         act = xz.dtype
-        dz, du, ddelta, dbc, ddt_b, dA2, dD, _ = scan_bwd(xz, delta, bc, dyg, packed, jobs, L, cstate)
+        dhlast = None
+        if shard is not None:
+            # adjoint carry: local Dh -> one all_gather -> compose the adjoint entering from the next shards
+            from . import seqshard
+            dh = scan_adjoint(xz, delta, bc, dyg, packed, jobs, L)
+            dhlast = seqshard.gather_adjoint(dh, dt_all, A2, jobs[1], jobs[2], shard)
+        dz, du, ddelta, dbc, ddt_b, dA2, dD, _ = scan_bwd(xz, delta, bc, dyg, packed, jobs, L, cstate, halo=halo,
+                                                          h0=h0, dhlast=dhlast)
         ld = xz.shape[-1]
         # dt_proj and x_proj backward (cuBLAS): d x_dbl = [W_dt^T d dt_raw ; dB ; dC]
         wdt_job = w_dt.index_select(0, pset_l)
@@ -426,12 +490,15 @@ class _BiMambaCoreFn(torch.autograd.Function):
         dxdbl[:, R:, :L] = dbc[..., :L].to(act)
         dw_dt = torch.zeros(w_dt.shape, device=xz.device, dtype=torch.float32)
         dw_dt.index_add_(0, pset_l, torch.bmm(ddelta[..., :L], xdbl[:, :R, :L].transpose(1, 2)).float())
-        u = conv_silu(xz, conv_w4, conv_b, jobs, L)
+        u = conv_silu(xz, conv_w4, conv_b, jobs, L, halo=halo)
         dw_x = torch.zeros(w_x.shape, device=xz.device, dtype=torch.float32)
         dw_x.index_add_(0, pset_l, torch.bmm(dxdbl[..., :L], u[..., :L].transpose(1, 2)).float())
         del u
         du_total = torch.baddbmm(du, wx_job.transpose(1, 2), dxdbl)
-        dx, dconv_w, dconv_b = conv_silu_bwd(xz, du_total, conv_w4, conv_b, jobs, L)
+        dx, dconv_w, dconv_b = conv_silu_bwd(xz, du_total, conv_w4, conv_b, jobs, L, halo=halo)
+        if shard is not None:       # the successor's first conv outputs read our edge samples: add their gradient
+            dhalo = conv_halo_grad(xz, du_total, halo, conv_w4, conv_b, jobs, L)
+            seqshard.exchange_halo_grad(dhalo, dx, L, jobs[0], jobs[2], shard)
         # several jobs (directions) may share one in-proj output: sum their gradients
         E = dx.shape[1]
         nseq, njobs = xz.shape[0], dx.shape[0]
@@ -445,11 +512,11 @@ class _BiMambaCoreFn(torch.autograd.Function):
             dxz[:, :E].index_add_(0, seq_l, dx)
             dxz[:, E:].index_add_(0, seq_l, dz)
         dxz[..., L:] = 0
-        return (dxz, dw_x.to(w_x.dtype), dw_dt.to(w_dt.dtype), dconv_w, dconv_b, ddt_b, dA2, dD, None, None)
+        return (dxz, dw_x.to(w_x.dtype), dw_dt.to(w_dt.dtype), dconv_w, dconv_b, ddt_b, dA2, dD, None, None, None)
 
 
-def bimamba_core(xz, w_x, w_dt, packed, jobs, L):
-    return _BiMambaCoreFn.apply(xz, w_x, w_dt, *packed, jobs, L)
+def bimamba_core(xz, w_x, w_dt, packed, jobs, L, shard=None):
+    return _BiMambaCoreFn.apply(xz, w_x, w_dt, *packed, jobs, L, shard)
 
 
 def microbench(which):

@@ -204,9 +204,7 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
     tied_out = ndir == 1 or (dirs[1].out_proj.weight is dirs[0].out_proj.weight and dirs[1].out_proj.bias is dirs[0].out_proj.bias)
     shard = seqshard.current()
     if grad:
-        if shard is not None and shard.world > 1:
-            raise NotImplementedError("caduceus_b200: sequence-sharded TRAINING is not wired yet (forward only)")
-        return _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out)
+        return _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out, shard)
     nw = 1 if tied_in else ndir
     jobs = CF.job_tables(B, nstrand, ndir, not tied_in, dev)
     Lp = CF.round_up(max(L, 1), 16)
@@ -310,7 +308,7 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
     return out
 
 
-def _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out):
+def _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out, shard=None):
     """Differentiable variant of `bimamba_inner`: the dense projections are plain autograd matmuls, everything
     between them (conv, x_proj, dt_proj, scan, gate) is ONE custom Function with hand-written backward kernels
     (CF.bimamba_core).  Same algebra, same job layout as the inference path."""
@@ -341,7 +339,7 @@ def _bimamba_inner_train(hidden, dirs, strategy, nstrand, act, tied_in, tied_out
     w_x = torch.stack([m.x_proj.weight.to(act) for m in dirs])
     w_dt = torch.stack([m.dt_proj.weight.to(act) for m in dirs])
     packed = pack_scan_params(dirs)
-    yg = CF.bimamba_core(xz, w_x, w_dt, packed, jobs, L)                           # (njobs, E, Lp)
+    yg = CF.bimamba_core(xz, w_x, w_dt, packed, jobs, L, shard)                    # (njobs, E, Lp)
     yg = yg.view(B, nstrand, ndir, E, Lp)[..., :L]
 
     outs = []

@@ -20,7 +20,10 @@ All scans are shard-local and start together, so the P ranks run concurrently: t
 Measured on 2 x B200 (L = 131072, D = 256, 16 layers, bf16 forward): PS 50.8 -> 32.7 ms, Ph 37.6 -> 23.2 ms.
 
 `sequence_parallel(group)` is the user-facing switch: inside it `bimamba_inner` (hence every Caduceus model of this
-package) treats its input as the local shard.
+package) treats its input as the local shard.  Training works the same way (see the "backward" block below): the
+forward keeps the TRUE carry (zero-carry state pass -> all_gather -> full scan from h0), the backward gathers the
+per-shard adjoints once and runs the ordinary backward kernel with (h0, dhlast); parameter gradients are then summed
+over the ranks with `all_reduce_grads`.
 """
 import contextlib
 
@@ -35,6 +38,9 @@ class ShardContext:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        # gloo (CPU tests, or several ranks sharing one GPU in CI) moves CUDA tensors through host memory; the
+        # production backend is NCCL, which takes the device buffers as they are
+        self.host_staged = dist.get_backend(group) == "gloo"
 
 
 def current():
@@ -55,6 +61,8 @@ def sequence_parallel(group=None):
 def _all_gather(t, ctx):
     """(world, *t.shape) — one collective, one output buffer."""
     t = t.contiguous()
+    if ctx.host_staged and t.is_cuda:
+        return _all_gather(t.cpu(), ctx).to(t.device)
     out = torch.empty((ctx.world,) + tuple(t.shape), device=t.device, dtype=t.dtype)
     dist.all_gather_into_tensor(out.view(ctx.world * t.shape[0], *t.shape[1:]) if t.dim() > 0 else out, t,
                                 group=ctx.group)
@@ -117,11 +125,65 @@ def compose_carry(h_all, dtsum_all, A2_job, rev_of_job, rank):
     return (torch.where(rev, w_r, w_f) * h_all).sum(0).contiguous()
 
 
-def gather_carry(hlast, dtsum, A2, pset_of_job, rev_of_job, ctx):
+def gather_carry(hlast, dtsum, A2, pset_of_job, rev_of_job, ctx, return_dtsum=False):
     """All-gather (H, sum dt) of the zero-carry pass and compose this rank's carry-in state (njobs, E, N)."""
     E, N = hlast.shape[1], hlast.shape[2]
     packed = torch.cat([hlast.reshape(hlast.shape[0], -1), dtsum], dim=1)       # one message per rank
     allv = _all_gather(packed, ctx)
     h_all = allv[:, :, :E * N].reshape(ctx.world, -1, E, N)
     dt_all = allv[:, :, E * N:]
-    return compose_carry(h_all, dt_all, A2.index_select(0, pset_of_job.long()), rev_of_job, ctx.rank)
+    h0 = compose_carry(h_all, dt_all, A2.index_select(0, pset_of_job.long()), rev_of_job, ctx.rank)
+    return (h0, dt_all.contiguous()) if return_dtsum else h0
+
+
+# ---- backward (sequence-sharded TRAINING) -------------------------------------------------------------------------
+# The adjoint e = dLoss/dh runs against the job's direction, so the roles swap: rank k's adjoint carry-in comes from
+# its logical SUCCESSORS.  With Dh_j = the gradient w.r.t. shard j's carry-in from shard j's own tokens
+# (csrc/scan_adjoint.cu) and the same per-shard decays exp2(A2 * sum dt_i) as the forward,
+#     dhlast_k = sum_{j after k} exp2(A2 * sum_{i between k and j} sum dt_i) * Dh_j
+# which is `compose_carry` with the direction flags inverted.  Parameter gradients are partial sums over the local
+# tokens: all-reduce them like DDP does (`all_reduce_grads`).
+def gather_adjoint(dh_local, dtsum_all, A2, pset_of_job, rev_of_job, ctx):
+    """All-gather Dh and compose this rank's adjoint carry-in dhlast (njobs, E, N)."""
+    dh_all = _all_gather(dh_local, ctx)                                          # (world, njobs, E, N)
+    return compose_carry(dh_all, dtsum_all, A2.index_select(0, pset_of_job.long()), 1 - rev_of_job.to(torch.int32),
+                         ctx.rank)
+
+
+def exchange_halo_grad(dhalo, dx, L, seq_of_job, rev_of_job, ctx):
+    """Backward of `gather_halo`: dhalo (njobs, E, 3) is this rank's gradient w.r.t. the 3 samples it borrowed from
+    its logical predecessor; add what the logical successor computed for OUR edge samples into dx (njobs, E, >=L)."""
+    from . import functional as CF
+    host = CF.JOB_HOST.get(seq_of_job.data_ptr())
+    rev_l = host[2] if host is not None else tuple(rev_of_job.tolist())
+    allv = _all_gather(dhalo, ctx)                                                # (world, njobs, E, 3)
+    # a left-to-right job's successor is rank+1 and borrowed our LAST three (same order); a right-to-left job's
+    # successor is rank-1 and borrowed our FIRST three in reversed order
+    fwd_ok, rev_ok = ctx.rank + 1 < ctx.world, ctx.rank - 1 >= 0
+    fwd_jobs = [j for j, r in enumerate(rev_l) if not r]
+    rev_jobs = [j for j, r in enumerate(rev_l) if r]
+    if fwd_ok and fwd_jobs:
+        dx[fwd_jobs, :, L - 3:L] += allv[ctx.rank + 1, fwd_jobs].to(dx.dtype)
+    if rev_ok and rev_jobs:
+        dx[rev_jobs, :, 0:3] += allv[ctx.rank - 1, rev_jobs].flip(-1).to(dx.dtype)
+    return dx
+
+
+def all_reduce_grads(module, ctx=None, group=None):
+    """Sum the parameter gradients over the sequence shards (each rank holds the partial sum over its own tokens)."""
+    group = ctx.group if ctx is not None else group
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1).float() for g in grads])
+    if flat.is_cuda and dist.get_backend(group) == "gloo":
+        host = flat.cpu()
+        dist.all_reduce(host, group=group)
+        flat = host.to(flat.device)
+    else:
+        dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -165,6 +165,23 @@ typedef struct {
 } cad_scan_fixup_args;
 int cad_bimamba_scan_fixup(const cad_scan_fixup_args* a, void* stream);
 
+/* ---- adjoint of the carry (sequence-sharded TRAINING, SURVEY.md §8e "Backward"): the gradient w.r.t. a shard's
+ *      carry-in state produced by the shard's own tokens (adjoint carry-in taken as zero),
+ *          dh[n] = sum_tau exp2(A2[n] * sum_{s<=tau} dt[s]) * C[tau,n] * dout[tau] * silu(z[tau])
+ *      — the transpose of cad_bimamba_scan_fixup, with the same decay cut-off.  One all_gather of dh (and the
+ *      forward's sum dt) lets every rank compose its true adjoint carry-in and run cad_bimamba_scan_bwd once.    */
+typedef struct {
+  const void* xz; const void* delta; const float* bc; const void* dout;
+  const float* dt_b; const float* A2;
+  const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;
+  float* dh;                /* (njobs, E, N), written for every entry */
+  int64_t L, E, N;
+  int64_t ldxz, ldd, ldbc, ldo;
+  int32_t nseq, njobs, io_dtype, channels_per_cta;
+  float   cutoff_log2;
+} cad_scan_adjoint_args;
+int cad_bimamba_scan_adjoint(const cad_scan_adjoint_args* a, void* stream);
+
 /* ---- backward of cad_bimamba_scan_fwd (replaces selective_scan_cuda.bwd).
  *      Inputs as the forward plus dout (njobs, E, ldo) and the forward's chunk_state.  Outputs:
  *        dz      (njobs, E, lddz)   gradient of the gate input z                               io dtype
@@ -172,14 +189,15 @@ int cad_bimamba_scan_fixup(const cad_scan_fixup_args* a, void* stream);
  *        ddelta  (njobs, E, lddd)   gradient w.r.t. dt_raw                                     io dtype
  *        dbc     (njobs, 2N, ldbc)  gradient w.r.t. B/C rows, fp32, ACCUMULATED (caller zero-fills)
  *        ddt_b, dDskip (P, E), dA2 (P, E, N)   fp32, ACCUMULATED (caller zero-fills)
- *        dh0     (njobs, E, N)      gradient w.r.t. the carry-in state, or NULL                              */
+ *        dh0     (njobs, E, N)      gradient w.r.t. the carry-in state, or NULL
+ *      dhlast (njobs, E, N) or NULL: gradient w.r.t. the END state (adjoint carry-in from the logically next shard). */
 typedef struct {
   const void*  xz; const void* delta; const float* bc; const void* dout;
   const float* conv_w; const float* conv_b; const float* dt_b; const float* A2; const float* Dskip;
   const int32_t* seq_of_job; const int32_t* pset_of_job; const int32_t* rev_of_job;
   const void*  halo; const float* h0; const float* chunk_state;
   void* dz; void* du; void* ddelta; float* dbc;
-  float* ddt_b; float* dA2; float* dDskip; float* dh0;
+  float* ddt_b; float* dA2; float* dDskip; float* dh0; const float* dhlast;
   int64_t L, E, N, K;
   int64_t ldxz, ldd, ldbc, ldo, lddz, lddu, lddd;
   int32_t nseq, njobs, npset, io_dtype, channels_per_cta;
@@ -228,6 +246,21 @@ typedef struct {
   int32_t nseq, njobs, io_dtype;
 } cad_conv_fwd_args;
 int cad_conv_silu_fwd(const cad_conv_fwd_args* a, void* stream);
+
+/* ---- "next" row N2: GPU-side hg38 batch preparation, integer / byte work, bit-exact.
+ *      raw (B, L) ASCII bytes of the FASTA slices -> data, target (B, L) int64:
+ *        optional per-row string reverse complement (ref:src/dataloaders/utils/rc.py:17-26),
+ *        char -> id through a 256-entry table (ref:caduceus/tokenization_caduceus.py:49-58; lower case folded),
+ *        N -> PAD (ref:src/dataloaders/datasets/hg38_dataset.py:211-212),
+ *        MLM masking from caller-supplied draws (ref:src/dataloaders/utils/mlm.py:4-32); masked == NULL: ids only. */
+typedef struct {
+  const uint8_t* raw; const uint8_t* rc_flags /* (B) or NULL */; const int32_t* char_to_id /* (256) */;
+  const uint8_t* masked; const uint8_t* replaced; const uint8_t* random_sel; const int64_t* random_words;
+  int64_t* data; int64_t* target;
+  int64_t B, L;
+  int64_t n_id, pad_id, mask_id;
+} cad_hg38_batch_args;
+int cad_hg38_batch_fwd(const cad_hg38_batch_args* a, void* stream);
 
 /* ---- micro-benchmarks of the pipes that bound the scan (MUFU ex2, FFMA), used by bench.py to quote
  *      "fraction of measured MUFU peak" beside the HBM fraction.  Writes ops/s.          */

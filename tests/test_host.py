@@ -35,7 +35,9 @@ def test_struct_sizes_match_header_layout():
                        ("cad_scan_fwd_args", _lib.ScanFwdArgs), ("cad_conv_fwd_args", _lib.ConvFwdArgs),
                        ("cad_add_norm_bwd_args", _lib.AddNormBwdArgs), ("cad_embedding_bwd_args", _lib.EmbeddingBwdArgs),
                        ("cad_scan_bwd_args", _lib.ScanBwdArgs), ("cad_conv_bwd_args", _lib.ConvBwdArgs),
-                       ("cad_conv_xproj_args", _lib.ConvXprojArgs), ("cad_scan_fixup_args", _lib.ScanFixupArgs)):
+                       ("cad_conv_xproj_args", _lib.ConvXprojArgs), ("cad_scan_fixup_args", _lib.ScanFixupArgs),
+                       ("cad_hg38_batch_args", _lib.Hg38BatchArgs),
+                       ("cad_scan_adjoint_args", _lib.ScanAdjointArgs)):
         names = []
         for decl in structs[cname].split(";"):
             for part in decl.split(","):

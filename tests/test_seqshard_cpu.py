@@ -125,3 +125,105 @@ def test_compose_carry_is_the_affine_composition():
         for j in range(world - 1, rank, -1):
             b = torch.exp2(A2[1] * S[j, 1][:, None]) * b + H[j, 1]
         assert torch.allclose(h0[0], f) and torch.allclose(h0[1], b)
+
+
+# ---- backward: adjoint carry + halo gradient exchange (sequence-sharded TRAINING) ------------------------------------
+def _bwd_worker(rank, world, port, L, out_q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p, data = make_problem(L)
+        dout = torch.randn(2, p["conv_b"].shape[0], L, generator=torch.Generator().manual_seed(5))
+        seq_of_job = torch.tensor([0, 0], dtype=torch.int32)
+        rev_of_job = torch.tensor([0, 1], dtype=torch.int32)
+        pset = torch.tensor([0, 0], dtype=torch.int32)
+        Ls = L // world
+        sl = slice(rank * Ls, (rank + 1) * Ls)
+        pl = {k: v.clone().requires_grad_() for k, v in p.items()}
+        xj = [data["x"][0, :, sl].clone().requires_grad_() for _ in range(2)]       # per-job copies -> per-job dx
+        z = data["z"][0, :, sl].clone().requires_grad_()
+        dtr, Bm, Cm = (data[k][:, :, sl].clone().requires_grad_() for k in ("dt_raw", "B", "C"))
+        with seqshard.sequence_parallel() as ctx:
+            # forward, the kernel contract of _BiMambaCoreFn.forward: halo, zero-carry state pass, gather, true-carry scan
+            halo = seqshard.gather_halo(data["x"][..., sl], Ls, seq_of_job, rev_of_job, ctx).requires_grad_()
+            with torch.no_grad():
+                st = [local_scan(xj[j], z, dtr[j], Bm[j], Cm[j], p, bool(rev_of_job[j]), halo=halo[j]) for j in range(2)]
+            h0, dt_all = seqshard.gather_carry(torch.stack([s[1] for s in st]), torch.stack([s[2] for s in st]),
+                                               p["A2"][None], pset, rev_of_job, ctx, return_dtsum=True)
+            h0 = h0.requires_grad_()
+            res = [local_scan(xj[j], z, dtr[j], Bm[j], Cm[j], pl, bool(rev_of_job[j]), halo=halo[j], h0=h0[j])
+                   for j in range(2)]
+            obj = sum((res[j][0] * dout[j, :, sl]).sum() for j in range(2))
+            # backward: Dh (what cad_bimamba_scan_adjoint computes) -> gather/compose -> backward with dhlast
+            dh = torch.autograd.grad(obj, h0, retain_graph=True)[0]
+            dhlast = seqshard.gather_adjoint(dh, dt_all, p["A2"][None], pset, rev_of_job, ctx)
+            (obj + sum((res[j][1] * dhlast[j]).sum() for j in range(2))).backward()
+            dx = torch.stack([t.grad for t in xj])
+            seqshard.exchange_halo_grad(halo.grad, dx, Ls, seq_of_job, rev_of_job, ctx)
+            lin = torch.nn.Module()
+            for k, v in pl.items():
+                lin.register_parameter(k, torch.nn.Parameter(v.detach().clone()))
+                getattr(lin, k).grad = v.grad.clone()
+            seqshard.all_reduce_grads(lin, ctx)
+        tok = torch.cat([dx.sum(0)[None], z.grad[None], dtr.grad], 0)                                        # (4, E, Ls)
+        bcg = torch.cat([Bm.grad, Cm.grad], 0)                                                             # (4, N, Ls)
+        g1 = [torch.empty_like(tok) for _ in range(world)]
+        g2 = [torch.empty_like(bcg) for _ in range(world)]
+        dist.all_gather(g1, tok)
+        dist.all_gather(g2, bcg)
+        if rank == 0:
+            out_q.put((torch.cat(g1, -1), torch.cat(g2, -1), {k: getattr(lin, k).grad for k in pl}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_backward_matches_unsharded(world):
+    L = 48 * world
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bwd_worker, args=(r, world, port, L, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    tok, bcg, pg = q.get()
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    p, data = make_problem(L)
+    dout = torch.randn(2, p["conv_b"].shape[0], L, generator=torch.Generator().manual_seed(5))
+    pl = {k: v.clone().requires_grad_() for k, v in p.items()}
+    x, z = data["x"][0].clone().requires_grad_(), data["z"][0].clone().requires_grad_()
+    dtr, Bm, Cm = (data[k].clone().requires_grad_() for k in ("dt_raw", "B", "C"))
+    sum((local_scan(x, z, dtr[j], Bm[j], Cm[j], pl, bool(j))[0] * dout[j]).sum() for j in range(2)).backward()
+    want_tok = torch.cat([x.grad[None], z.grad[None], dtr.grad], 0)
+    want_bc = torch.cat([Bm.grad, Cm.grad], 0)
+    assert torch.allclose(tok, want_tok, rtol=1e-4, atol=1e-5), (tok - want_tok).abs().max()
+    assert torch.allclose(bcg, want_bc, rtol=1e-4, atol=1e-5), (bcg - want_bc).abs().max()
+    for k in pl:
+        assert torch.allclose(pg[k], pl[k].grad, rtol=1e-4, atol=1e-5), (k, (pg[k] - pl[k].grad).abs().max())
+
+
+def test_conv_halo_grad_matches_autograd():
+    """CF.conv_halo_grad (plain torch, used by the sharded backward) vs autograd through the conv + SiLU definition."""
+    from caduceus_b200 import functional as CF
+    g = torch.Generator().manual_seed(2)
+    nseq, E, L, P = 2, 5, 11, 2
+    xz = torch.randn(nseq, 2 * E, 16, generator=g)
+    jobs = (torch.tensor([0, 0, 1, 1], dtype=torch.int32), torch.tensor([0, 1, 0, 1], dtype=torch.int32),
+            torch.tensor([0, 1, 1, 0], dtype=torch.int32))
+    w, b = torch.randn(P, E, 4, generator=g), torch.randn(P, E, generator=g)
+    halo = torch.randn(4, E, 3, generator=g).requires_grad_()
+    du = torch.randn(4, E, 16, generator=g)
+    obj = 0.0
+    for j in range(4):
+        x = xz[jobs[0][j], :E, :L]
+        du_j = du[j, :, :L]
+        if jobs[2][j]:
+            x, du_j = x.flip(-1), du_j.flip(-1)
+        xp = torch.cat([halo[j], x], dim=1)
+        c = b[jobs[1][j]][:, None] + sum(w[jobs[1][j]][:, k:k + 1] * xp[:, k:k + L] for k in range(4))
+        obj = obj + (F.silu(c) * du_j).sum()
+    obj.backward()
+    got = CF.conv_halo_grad(xz, du, halo.detach(), w, b, jobs, L)
+    assert torch.allclose(got, halo.grad, rtol=1e-5, atol=1e-6), (got - halo.grad).abs().max()
