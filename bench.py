@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--graph", action="store_true",
                     help="replay the forward from a CUDA graph (single-GPU / replica forward only; helps short sequences)")
     ap.add_argument("--scan-tok", type=int, default=0, choices=[0, 8, 16], help="tokens per lane of the scan kernel (tuning)")
+    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4],
+                    help="forward-scan kernel variant (cad_scan_fwd_args.variant); default: env CAD_SCAN_VARIANT / library default")
     ap.add_argument("--shard", default="none", choices=["none", "seq"],
                     help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
     return ap.parse_args()
@@ -167,6 +169,8 @@ def run_b200(a):
     import torch.distributed as dist
     import caduceus
     from caduceus_b200 import functional as CF
+    if a.scan_variant is not None:
+        CF.SCAN_VARIANT = a.scan_variant
 
     CF.SCAN_TOKENS_PER_LANE = a.scan_tok
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -333,6 +337,7 @@ def run_b200(a):
         calls_per_launch = 2 if a.model == "ps" else 1
         bytes_per_launch = 2 * (8 * E + 4 * N) * calls_per_launch * a.batch * a.seqlen
         scan_ms = [s.elapsed_time(e) for s, e in scan_events]
+        scan_v4 = CF.SCAN_VARIANT == 4 and not train and not shard_seq      # v4 covers the plain inference call only
         avg_scan_ms = sum(scan_ms) / max(len(scan_ms), 1)
         peaks = {}
         try:
@@ -345,10 +350,10 @@ def run_b200(a):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
             if a.seqlen == 131072 and a.d_model == 256 and a.batch == 1 and not shard_seq:
-                traffic = tj[a.model]["dram_bytes_per_launch"]
+                traffic = tj[a.model + ("_v4" if scan_v4 else "")]["dram_bytes_per_launch"]
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "bimamba_scan_fwd_kernel", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "bimamba_scan_fwd_v4_kernel" if scan_v4 else "bimamba_scan_fwd_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "6.65 TB/s (of fallback)",
@@ -379,7 +384,8 @@ def run_b200(a):
             "config": {"workload": workload_name(a), "parallelism": (f"sp{world} (one sequence sharded on the sequence axis, 2 tiny all_gathers per layer)"
                                        if shard_seq else f"dp{world} (independent sequences per GPU)"),
                        "l2": "per-step working set > 1 GB >> 126 MB L2; 4 rotating input batches",
-                       "launch": "CUDA graph replay" if graphed else "eager"},
+                       "launch": "CUDA graph replay" if graphed else "eager",
+                       "scan_variant": 4 if scan_v4 else 3},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": a.batch * a.seqlen * 8 * world,
                     "d2h_bytes_per_step": (4 if train else a.batch * a.seqlen * cfg.vocab_size * 4) * world},

@@ -28,6 +28,7 @@
 //   profiles: profiles/r1_v1_scan_ncu_summary.txt (v1: 20.8 warp-instructions per element, 43 % issue utilisation)
 //   -> profiles/r1_v3_scan_and_bwd_ncu_summary.txt (11.4 instructions per element, MUFU pipe 53 %, issue 57 %).
 #include "scan_common.cuh"
+#include "scan_fwd_v4.cuh"
 
 namespace cad {
 
@@ -353,6 +354,35 @@ static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
   return 0;
 }
 
+// ---- v4: two channels per warp, packed fp32 (scan_fwd_v4.cuh) ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(v4::kMaxG4 * 32, 1)
+bimamba_scan_fwd_v4_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ unsigned char smem_raw[];
+  v4::kernel_body<T>(a, &tmap, smem_raw);
+}
+
+template <typename T>
+static int launch_scan_v4(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
+  CUtensorMap tmap;
+  if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * v4::NST, a.ldbc, a.L, 2 * v4::NST, v4::CH) != 0) return -1;
+  const size_t smem = v4::smem_bytes(G, sizeof(T));
+  auto kern = bimamba_scan_fwd_v4_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(v4): %s", cudaGetErrorString(e)); return (int)e; }
+  const int64_t npair = a.E / 2;
+  dim3 grid((unsigned)((npair + G - 1) / G), (unsigned)a.njobs);
+  kern<<<grid, G * 32, smem, stream>>>(a, tmap);
+  CAD_LAUNCH_CHECK();
+  return 0;
+}
+
+// v4 covers the inference configuration only (see scan_fwd_v4.cuh "scope")
+static bool v4_supported(const cad_scan_fwd_args& a) {
+  return a.io_dtype != CAD_F32 && a.N == v4::NST && a.E % 2 == 0 && !a.halo && !a.h0 && !a.hlast && !a.dtsum &&
+         !a.chunk_state && !a.state_only && (a.tokens_per_lane == 0 || a.tokens_per_lane == 16);
+}
+
 }  // namespace cad
 
 extern "C" int cad_scan_chunk_len(void) { return cad::kChunk; }
@@ -373,6 +403,24 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
               "cad_bimamba_scan_fwd: xz/delta/bc/out must be 16-byte aligned");
   CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4, "cad_bimamba_scan_fwd: variant must be 0, 3 or 4");
+  if (a->variant == 4) {
+    CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
+                "halo / h0 / hlast / dtsum / chunk_state / state_only");
+    int G4 = a->channels_per_cta;       // here: channel PAIRS (warps) per CTA
+    if (G4 <= 0) {
+      const int sms = cad_sm_count() > 0 ? cad_sm_count() : 148;
+      long best = -1;
+      for (int g = 1; g <= v4::kMaxG4; ++g) {      // one CTA per SM: minimise the busiest SM's pair count
+        const long ctas = (long)a->njobs * ((a->E / 2 + g - 1) / g);
+        const long cost = ((ctas + sms - 1) / sms) * g;
+        if (best < 0 || cost <= best) { best = cost; G4 = g; }
+      }
+    }
+    CAD_REQUIRE(G4 >= 1 && G4 <= v4::kMaxG4, "cad_bimamba_scan_fwd: channels_per_cta must be in [1, %d] for variant 4", v4::kMaxG4);
+    if (a->io_dtype == CAD_BF16) return launch_scan_v4<__nv_bfloat16>(*a, G4, stream);
+    return launch_scan_v4<__half>(*a, G4, stream);
+  }
   int G = a->channels_per_cta;
   if (G <= 0) {
     // two CTAs are resident per SM; the busiest SM carries ceil(ctas / sms) * g channels: minimise that

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CAD_ABI_VERSION 1
+#define CAD_ABI_VERSION 2
 
 typedef enum { CAD_F32 = 0, CAD_F16 = 1, CAD_BF16 = 2 } cad_dtype;
 
@@ -145,6 +145,9 @@ typedef struct {
   int32_t channels_per_cta; /* 0 = library picks so that the grid is ~ a multiple of the SM count */
   int32_t state_only;       /* 1: only hlast / dtsum are produced (pass 1 of a sequence-sharded scan); out may be NULL */
   int32_t tokens_per_lane;  /* 0 = default (16); 8 = 256-token chunks with more CTAs per SM (16-bit I/O, no chunk_state) */
+  int32_t variant;          /* 0 = library default; 3 = one channel per warp; 4 = two channels per warp with packed
+                               fp32 (inference only: 16-bit I/O, even E, no sharding hooks / saved states — an error
+                               otherwise; channels_per_cta then counts channel PAIRS) */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */

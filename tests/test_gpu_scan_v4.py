@@ -1,0 +1,100 @@
+"""GPU parity of the paired-channel scan kernel (cad_scan_fwd_args.variant = 4, csrc/scan_fwd_v4.cuh), through the C-ABI:
+against the float64 restatement at the kernel boundary (tests/test_emu_scan_v4.py::boundary_ref — the same checker the
+CPU emulation of this kernel is held to), against the one-channel-per-warp kernel (variant 3) on identical inputs,
+and end to end through the model against the fixture produced by the reference's own code."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, tol
+from test_emu_scan_v4 import _problem, boundary_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run(L, E, spec, dtype, G, seed, variant):
+    from caduceus_b200 import functional as CF
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, seed)
+    d = lambda t: t.to(DEV).contiguous()   # noqa: E731
+    out, _, _, _ = CF.scan_fwd(d(xz), d(delta), d(bc), tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)),
+                               tuple(d(t) for t in tabs), L, channels_per_cta=G, variant=variant)
+    torch.cuda.synchronize()
+    f = lambda t: t.float().numpy()   # noqa: E731
+    ref = boundary_ref(f(xz), f(delta), f(bc), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk),
+                       [s for s, _, _ in spec], [q for _, q, _ in spec], [r for _, _, r in spec], L)
+    return out[..., :L].float().cpu().numpy(), ref
+
+
+def _check(got, ref, dtype, what):
+    # bf16: tighter than the reference's own 3e-2 / 5e-2 (ref:caduceus/tests/test_rcps.py:36); fp16: the reference's.
+    # (the CPU emulation of the same source is held to 1.5 output ulps; here MUFU tanh/ex2/lg2 approximations add noise)
+    rtol, atol = (1e-2, 1e-2) if dtype == torch.bfloat16 else tol(dtype)
+    err = np.abs(got - ref)
+    bound = atol + rtol * np.abs(ref)
+    assert np.isfinite(got).all(), what
+    assert (err <= bound).all(), f"{what}: max err {err.max():.3e}, worst excess {(err - bound).max():.3e}"
+
+
+@pytest.mark.parametrize("L", [1, 17, 511, 512, 513, 1030, 2300])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_v4_vs_boundary_restatement_ragged_lengths(L, rev):
+    got, ref = _run(L, 64, [(0, 0, rev)], torch.bfloat16, 0, 100 + L, 4)
+    _check(got, ref, torch.bfloat16, f"v4 L={L} rev={rev}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("G", [1, 2, 5, 7])
+def test_v4_ps_job_layout_and_cta_shapes(dtype, G):
+    """Caduceus-PS job order (2 sequences x 2 parameter sets, rev = direction XOR strand), E/2 = 19 pairs so the last
+    CTA has idle warps for every G, five chunks with a ragged tail."""
+    spec = [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0)]
+    got, ref = _run(2300, 38, spec, dtype, G, 7, 4)
+    _check(got, ref, dtype, f"v4 G={G} {dtype}")
+
+
+def test_v4_agrees_with_v3_on_identical_inputs():
+    spec = [(0, 0, 0), (0, 1, 1)]
+    g4, ref = _run(5000, 128, spec, torch.bfloat16, 0, 3, 4)
+    g3, _ = _run(5000, 128, spec, torch.bfloat16, 0, 3, 3)
+    _check(g4, ref, torch.bfloat16, "v4")
+    _check(g3, ref, torch.bfloat16, "v3")
+    # both round the same fp32 value to bf16 up to MUFU / summation-order noise: at most a few bf16 ulps apart
+    assert np.abs(g4 - g3).max() <= 2e-3 + 2.0 ** -6 * np.abs(ref).max()
+
+
+def test_v4_rejects_what_it_does_not_cover():
+    from caduceus_b200 import functional as CF
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(100, 8, [(0, 0, 0)], torch.float32, 0)
+    d = lambda t: t.to(DEV).contiguous()   # noqa: E731
+    with pytest.raises(RuntimeError, match="variant 4"):
+        CF.scan_fwd(d(xz), d(delta), d(bc), tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)),
+                    tuple(d(t) for t in tabs), 100, variant=4)
+
+
+@pytest.mark.parametrize("tag", ["ps_small", "ph_config0"])
+def test_model_forward_with_v4_vs_reference_fixture(tag):
+    """The whole model with the scan forced to variant 4, against the logits the reference's own code produced."""
+    import caduceus
+    from caduceus_b200 import functional as CF
+    fx = golden(f"model_{tag}.pt")
+    cfg = caduceus.CaduceusConfig(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in fx["config"].items()})
+    model = caduceus.CaduceusForMaskedLM(cfg)
+    model.load_state_dict(fx["state_dict"])
+    model = model.to(DEV).to(torch.bfloat16).eval()
+    launches = []
+    orig = CF.scan_variant
+    try:
+        CF.SCAN_VARIANT = 4
+        CF.scan_variant = lambda a: launches.append(orig(a)) or launches[-1]
+        with torch.no_grad():
+            logits = model(fx["input_ids"].to(DEV)).logits.float().cpu()
+    finally:
+        CF.SCAN_VARIANT = 0
+        CF.scan_variant = orig
+    assert launches and all(v == 4 for v in launches), launches
+    # same criterion as test_gpu_parity.py::test_model_low_precision_vs_reference_fixture (16-bit stack vs fp32 fixture)
+    rtol, atol = tol(torch.bfloat16)
+    scale = fx["logits"].abs().max().item()
+    err = (logits - fx["logits"]).abs().max().item()
+    assert err <= atol + rtol * scale * 4, (err, scale)
