@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--graph", action="store_true",
                     help="replay the forward from a CUDA graph (single-GPU / replica forward only; helps short sequences)")
     ap.add_argument("--scan-tok", type=int, default=0, choices=[0, 8, 16], help="tokens per lane of the scan kernel (tuning)")
-    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4],
+    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4, 5, 6],
                     help="forward-scan kernel variant (cad_scan_fwd_args.variant); default: env CAD_SCAN_VARIANT / library default")
     ap.add_argument("--shard", default="none", choices=["none", "seq"],
                     help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
@@ -385,7 +385,7 @@ def run_b200(a):
                                        if shard_seq else f"dp{world} (independent sequences per GPU)"),
                        "l2": "per-step working set > 1 GB >> 126 MB L2; 4 rotating input batches",
                        "launch": "CUDA graph replay" if graphed else "eager",
-                       "scan_variant": 4 if scan_v4 else 3},
+                       "scan_variant": 4 if scan_v4 else (CF.SCAN_VARIANT or 3)},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": a.batch * a.seqlen * 8 * world,
                     "d2h_bytes_per_step": (4 if train else a.batch * a.seqlen * cfg.vocab_size * 4) * world},

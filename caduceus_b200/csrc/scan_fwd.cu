@@ -47,7 +47,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // One chunk of one channel.  TAIL: the chunk straddles the sequence end (per-token masks, halo in the pad).
-template <typename T, int N, int TOK, bool REV, bool TAIL, bool STATE_ONLY>
+// PK: 0 = scalar fp32 state loop; 1 = token pairs packed (FMUL2 for dt*A2 and du*B, FFMA2 for the C.h accumulation —
+// adjacent PHYSICAL tokens of the lane's segment sit in aligned register pairs, the scalar A2 is the broadcast operand);
+// 2 = 1 + the exp2 of state n+1 issued behind state n's FMA chains and shuffles (two `a` buffers, loop unrolled by 2).
+template <typename T, int N, int TOK, bool REV, bool TAIL, bool STATE_ONLY, int PK>
 __device__ __forceinline__ void scan_chunk(
     const cad_scan_fwd_args& a, const ScanSmem& sm, int lane, int seg, const uint32_t (&poff)[TOK / 4],
     const T* __restrict__ xrow, const T* __restrict__ zrow, const T* __restrict__ drow, T* __restrict__ orow,
@@ -125,56 +128,146 @@ __device__ __forceinline__ void scan_chunk(
   mbar_wait(sm.bar, parity);
   const uint32_t tile_s = smem_u32(sm.tile);
   const uint32_t a2_s = smem_u32(my_a2), carry_s = smem_u32(my_carry);
+  if constexpr (PK == 0) {
+  #pragma unroll 1
+    for (int n = 0; n < N; ++n) {
+      const float A2n = lds32(a2_s + 4 * n);
+      const float cin = lds32(carry_s + 4 * n);
+      float av[TOK], bv[TOK];
+      float hl = (lane == 0) ? cin : 0.f;
+      {
+        const uint32_t rowp = tile_s + n * (CH * 4);
+  #pragma unroll
+        for (int k = 0; k < TOK / 4; ++k) {
+          const float4 q = lds128(rowp + poff[k]);
+          const float bq[4] = {q.x, q.y, q.z, q.w};
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;     // logical item of physical token 4k+e
+            av[i] = ex2(dt[i] * A2n);
+            bv[i] = du[i] * bq[e];
+          }
+        }
+  #pragma unroll
+        for (int i = 0; i < TOK; ++i) hl = fmaf(av[i], hl, bv[i]);
+      }
+      float P = ex2(A2n * dsum);
+      scan_step_up<1>(P, hl, lane);
+      scan_step_up<2>(P, hl, lane);
+      scan_step_up<4>(P, hl, lane);
+      scan_step_up<8>(P, hl, lane);
+      scan_step_up<16>(P, hl, lane);
+      float h = __shfl_up_sync(0xffffffffu, hl, 1);
+      if (lane == 0) h = cin;
+      if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
+      if (!STATE_ONLY) {
+        const uint32_t rowp = tile_s + (N + n) * (CH * 4);
+        float4 cq[TOK / 4];
+  #pragma unroll
+        for (int k = 0; k < TOK / 4; ++k) cq[k] = lds128(rowp + poff[k]);
+        // walk the segment in LOGICAL order (physical pieces backwards for a reversed job)
+  #pragma unroll
+        for (int kk = 0; kk < TOK / 4; ++kk) {
+          const int k = REV ? TOK / 4 - 1 - kk : kk;
+          const float ce[4] = {cq[k].x, cq[k].y, cq[k].z, cq[k].w};
+  #pragma unroll
+          for (int ee = 0; ee < 4; ++ee) {
+            const int e = REV ? 3 - ee : ee;
+            const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;
+            h = fmaf(av[i], h, bv[i]);
+            y[i] = fmaf(ce[e], h, y[i]);
+          }
+        }
+      }
+    }
+  } else {
+    using v4::fma2; using v4::mul2; using v4::splat; using v4::ex2_2;
+    constexpr int NP = TOK / 2;
+    auto lgc = [](int p) { return REV ? TOK - 1 - p : p; };          // physical token of the segment -> logical item
+    float2 dt2[NP], du2[NP], y2[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      dt2[j] = make_float2(dt[lgc(2 * j)], dt[lgc(2 * j + 1)]);
+      du2[j] = make_float2(du[lgc(2 * j)], du[lgc(2 * j + 1)]);
+      y2[j] = make_float2(y[lgc(2 * j)], y[lgc(2 * j + 1)]);
+    }
+    auto compute_a = [&](int n, float2 (&av2)[NP]) {
+      const float A2n = lds32(a2_s + 4 * n);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) av2[j] = ex2_2(mul2(dt2[j], splat(A2n)));
+    };
+    auto run_state = [&](int n, const float2 (&av2)[NP]) {
+      const float A2n = lds32(a2_s + 4 * n);
+      const float cin = lds32(carry_s + 4 * n);
+      float2 bv2[NP];
+      float hl = (lane == 0) ? cin : 0.f;
+      {
+        const uint32_t rowp = tile_s + n * (CH * 4);
+#pragma unroll
+        for (int k = 0; k < TOK / 4; ++k) {
+          const float4 q = lds128(rowp + poff[k]);
+          bv2[2 * k] = mul2(du2[2 * k], make_float2(q.x, q.y));
+          bv2[2 * k + 1] = mul2(du2[2 * k + 1], make_float2(q.z, q.w));
+        }
+#pragma unroll
+        for (int i = 0; i < TOK; ++i) {                              // logical order
+          const int p = REV ? TOK - 1 - i : i;
+          const float aa = (p & 1) ? av2[p >> 1].y : av2[p >> 1].x;
+          const float bb = (p & 1) ? bv2[p >> 1].y : bv2[p >> 1].x;
+          hl = fmaf(aa, hl, bb);
+        }
+      }
+      float P = ex2(A2n * dsum);
+      scan_step_up<1>(P, hl, lane);
+      scan_step_up<2>(P, hl, lane);
+      scan_step_up<4>(P, hl, lane);
+      scan_step_up<8>(P, hl, lane);
+      scan_step_up<16>(P, hl, lane);
+      float h = __shfl_up_sync(0xffffffffu, hl, 1);
+      if (lane == 0) h = cin;
+      if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
+      if (!STATE_ONLY) {
+        const uint32_t rowp = tile_s + (N + n) * (CH * 4);
+        float4 cq[TOK / 4];
+#pragma unroll
+        for (int k = 0; k < TOK / 4; ++k) cq[k] = lds128(rowp + poff[k]);
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) {                            // pairs in logical order
+          const int j = REV ? NP - 1 - jj : jj;
+          float2 hp;
+          if (REV) {
+            h = fmaf(av2[j].y, h, bv2[j].y); hp.y = h;
+            h = fmaf(av2[j].x, h, bv2[j].x); hp.x = h;
+          } else {
+            h = fmaf(av2[j].x, h, bv2[j].x); hp.x = h;
+            h = fmaf(av2[j].y, h, bv2[j].y); hp.y = h;
+          }
+          const float4 c4 = cq[j >> 1];
+          const float2 cp = (j & 1) ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
+          y2[j] = fma2(cp, hp, y2[j]);
+        }
+      }
+    };
+    if constexpr (PK == 1) {
 #pragma unroll 1
-  for (int n = 0; n < N; ++n) {
-    const float A2n = lds32(a2_s + 4 * n);
-    const float cin = lds32(carry_s + 4 * n);
-    float av[TOK], bv[TOK];
-    float hl = (lane == 0) ? cin : 0.f;
-    {
-      const uint32_t rowp = tile_s + n * (CH * 4);
-#pragma unroll
-      for (int k = 0; k < TOK / 4; ++k) {
-        const float4 q = lds128(rowp + poff[k]);
-        const float bq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;     // logical item of physical token 4k+e
-          av[i] = ex2(dt[i] * A2n);
-          bv[i] = du[i] * bq[e];
-        }
+      for (int n = 0; n < N; ++n) {
+        float2 av2[NP];
+        compute_a(n, av2);
+        run_state(n, av2);
       }
-#pragma unroll
-      for (int i = 0; i < TOK; ++i) hl = fmaf(av[i], hl, bv[i]);
-    }
-    float P = ex2(A2n * dsum);
-    scan_step_up<1>(P, hl, lane);
-    scan_step_up<2>(P, hl, lane);
-    scan_step_up<4>(P, hl, lane);
-    scan_step_up<8>(P, hl, lane);
-    scan_step_up<16>(P, hl, lane);
-    float h = __shfl_up_sync(0xffffffffu, hl, 1);
-    if (lane == 0) h = cin;
-    if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
-    if (!STATE_ONLY) {
-      const uint32_t rowp = tile_s + (N + n) * (CH * 4);
-      float4 cq[TOK / 4];
-#pragma unroll
-      for (int k = 0; k < TOK / 4; ++k) cq[k] = lds128(rowp + poff[k]);
-      // walk the segment in LOGICAL order (physical pieces backwards for a reversed job)
-#pragma unroll
-      for (int kk = 0; kk < TOK / 4; ++kk) {
-        const int k = REV ? TOK / 4 - 1 - kk : kk;
-        const float ce[4] = {cq[k].x, cq[k].y, cq[k].z, cq[k].w};
-#pragma unroll
-        for (int ee = 0; ee < 4; ++ee) {
-          const int e = REV ? 3 - ee : ee;
-          const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;
-          h = fmaf(av[i], h, bv[i]);
-          y[i] = fmaf(ce[e], h, y[i]);
-        }
+    } else {
+      float2 avA[NP], avB[NP];
+      compute_a(0, avA);
+#pragma unroll 1
+      for (int n = 0; n < N; n += 2) {
+        compute_a(n + 1, avB);
+        run_state(n, avA);
+        if (n + 2 < N) compute_a(n + 2, avA);
+        run_state(n + 1, avB);
       }
     }
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { y[lgc(2 * j)] = y2[j].x; y[lgc(2 * j + 1)] = y2[j].y; }
   }
 
   // ---- 4. hand the tile back: everyone is done reading -> request the next chunk -------------------------
@@ -202,7 +295,7 @@ __device__ __forceinline__ void scan_chunk(
   (void)EPV;
 }
 
-template <typename T, int N, int TOK, bool REV, bool STATE_ONLY>
+template <typename T, int N, int TOK, bool REV, bool STATE_ONLY, int PK>
 __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUtensorMap* tmap, int job, int seq,
                                          int pset, const ScanSmem& sm) {
   constexpr int CH = 32 * TOK;
@@ -292,11 +385,11 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     const T* pre_cur = pre_ptr((int)(c & 1));
     T* pre_next = pre_ptr((int)((c + 1) & 1));
     if (tail)
-      scan_chunk<T, N, TOK, REV, true, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, TOK, REV, true, STATE_ONLY, PK>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                   prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
                                   tseg_next);
     else
-      scan_chunk<T, N, TOK, REV, false, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, TOK, REV, false, STATE_ONLY, PK>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                    prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
                                    tseg_next);
     parity ^= 1;
@@ -317,9 +410,8 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
   }
 }
 
-template <typename T, int N, int TOK, bool STATE_ONLY>
-__global__ void __launch_bounds__(kMaxG * 32, (TOK == 16 ? 2 : 4))
-bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
+template <typename T, int N, int TOK, bool STATE_ONLY, int PK>
+__device__ __forceinline__ void scan_kernel_body(const cad_scan_fwd_args& a, const CUtensorMap* tmap) {
   extern __shared__ unsigned char smem_raw[];
   // the swizzled TMA destination must be 1024-byte aligned
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -333,11 +425,24 @@ bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUten
   if (threadIdx.x == 0) mbar_init(sm.bar, 1);
   const int job = blockIdx.y;
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
-  if (rev) scan_job<T, N, TOK, true, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
-  else     scan_job<T, N, TOK, false, STATE_ONLY>(a, &tmap, job, seq, pset, sm);
+  if (rev) scan_job<T, N, TOK, true, STATE_ONLY, PK>(a, tmap, job, seq, pset, sm);
+  else     scan_job<T, N, TOK, false, STATE_ONLY, PK>(a, tmap, job, seq, pset, sm);
 }
 
-template <typename T, int N, int TOK>
+template <typename T, int N, int TOK, bool STATE_ONLY, int PK = 0>
+__global__ void __launch_bounds__(kMaxG * 32, (TOK == 16 ? 2 : 4))
+bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
+  scan_kernel_body<T, N, TOK, STATE_ONLY, PK>(a, &tmap);
+}
+
+// PK = 2 keeps two `a` buffers live: 144 registers (14 warps x 32 x 144 = 64512 <= 65536, still 2 CTAs per SM)
+template <typename T, int N, bool STATE_ONLY>
+__global__ void __maxnreg__(144)
+bimamba_scan_fwd_pipe_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
+  scan_kernel_body<T, N, 16, STATE_ONLY, 2>(a, &tmap);
+}
+
+template <typename T, int N, int TOK, int PK = 0>
 static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
   constexpr int CH = 32 * TOK;
   CUtensorMap tmap;
@@ -345,7 +450,11 @@ static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
 
   const size_t pre_bytes = sizeof(T) == 2 ? (size_t)2 * G * 3 * CH * sizeof(T) : 0;
   const size_t smem = 1024 + (size_t)2 * N * CH * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16 + pre_bytes;
-  auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, TOK, true> : bimamba_scan_fwd_kernel<T, N, TOK, false>;
+  void (*kern)(const cad_scan_fwd_args, const CUtensorMap);
+  if constexpr (PK == 2 && TOK == 16)
+    kern = a.state_only ? bimamba_scan_fwd_pipe_kernel<T, N, true> : bimamba_scan_fwd_pipe_kernel<T, N, false>;
+  else
+    kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, TOK, true, PK> : bimamba_scan_fwd_kernel<T, N, TOK, false, PK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
@@ -403,7 +512,7 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
               "cad_bimamba_scan_fwd: xz/delta/bc/out must be 16-byte aligned");
   CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4, "cad_bimamba_scan_fwd: variant must be 0, 3 or 4");
+  CAD_REQUIRE(a->variant == 0 || (a->variant >= 3 && a->variant <= 6), "cad_bimamba_scan_fwd: variant must be 0 or 3..6");
   if (a->variant == 4) {
     CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
                 "halo / h0 / hlast / dtsum / chunk_state / state_only");
@@ -439,6 +548,8 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   if (tok == 0) tok = 16;
   CAD_REQUIRE(tok == 16 || tok == 8, "cad_bimamba_scan_fwd: tokens_per_lane must be 0, 8 or 16");
   if (a->chunk_state || a->io_dtype == CAD_F32) tok = 16;
+  if (tok == 16 && a->variant == 5) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 1>(*a, G, stream)); }
+  if (tok == 16 && a->variant == 6) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 2>(*a, G, stream)); }
   if (tok == 16) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16>(*a, G, stream)); }
   else if (a->io_dtype == CAD_BF16) return launch_scan<__nv_bfloat16, 16, 8>(*a, G, stream);
   else return launch_scan<__half, 16, 8>(*a, G, stream);
