@@ -126,6 +126,19 @@ __device__ __forceinline__ void scan_chunk(
 
   // ---- 3. the scan, one state at a time, on the TMA-staged B/C tile ------------------------------------
   mbar_wait(sm.bar, parity);
+  if (a.stagger > 0) {
+    // De-phase the warps that share a scheduler.  Every warp's state iteration is a MUFU burst (16 exp2) followed by
+    // ~300 cycles of dependent FMA / shuffle latency; warps that start a chunk together stay in lock-step (the MUFU
+    // pipe interleaves their bursts fairly), so the pipe idles while ALL of them sit in the latency phase.  Holding
+    // every second warp of a scheduler back by about half an iteration lets one group's bursts fill the other's gaps.
+    const int w = threadIdx.x >> 5;
+    const int mode = a.stagger >> 16, cyc = a.stagger & 0xffff;
+    const int grp = mode == 0 ? ((w >> 2) & 1) : (mode == 1 ? (w & 1) : (w % 3));
+    if (grp) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)cyc * grp) {}
+    }
+  }
   const uint32_t tile_s = smem_u32(sm.tile);
   const uint32_t a2_s = smem_u32(my_a2), carry_s = smem_u32(my_carry);
   if constexpr (PK == 0) {

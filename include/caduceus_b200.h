@@ -150,6 +150,9 @@ typedef struct {
                                (144 registers); 4 = two channels per warp with packed fp32 (inference only: 16-bit I/O,
                                even E, no sharding hooks / saved states — an error otherwise; channels_per_cta then
                                counts channel PAIRS).  Variants 5 / 6 apply to 16 tokens per lane. */
+  int32_t stagger;          /* variants 3 / 5 / 6: 0 = off; else bits 0-15 = cycles by which every second warp of a
+                               scheduler is held back at the start of each chunk's state loop, bits 16-17 = grouping
+                               (0: (warp >> 2) & 1, 1: warp & 1, 2: warp % 3 with 1x / 2x the delay) */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
