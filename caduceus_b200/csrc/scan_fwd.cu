@@ -27,6 +27,8 @@
 //   sum(dt) only, no output), REV/TAIL specialisations (reversed jobs; the one chunk that straddles the sequence end).
 //   profiles: profiles/r1_v1_scan_ncu_summary.txt (v1: 20.8 warp-instructions per element, 43 % issue utilisation)
 //   -> profiles/r1_v3_scan_and_bwd_ncu_summary.txt (11.4 instructions per element, MUFU pipe 53 %, issue 57 %).
+#include <type_traits>
+
 #include "scan_common.cuh"
 #include "scan_fwd_v4.cuh"
 
@@ -261,7 +263,90 @@ __device__ __forceinline__ void scan_chunk(
         }
       }
     };
-    if constexpr (PK == 1) {
+    // PK 3 / 4 — no replay: the zero-state pass also accumulates y += C.h_local and the running decay
+    // pc_t = prod_{s<=t} a_s; after the warp scan the carry-in enters as 8 INDEPENDENT packed FMAs
+    // y_t += (C_t pc_t) * h_in.  Against the replay form this drops the second 16-step dependent chain, the stored
+    // a / b arrays (32 registers) and the extra exp2 of the segment decay (the aggregate IS pc_15); it adds one FMUL
+    // (pc) and half a packed FMUL (C*pc) per element, issued in the MUFU-bound phase where issue slots are idle.
+    // NS = 2 (PK 4) runs two states side by side so that their shuffle rounds overlap.
+    auto run_states_pc = [&](int n0, auto ns_tag) {
+      constexpr int NS = decltype(ns_tag)::value;
+      float A2n[NS], cin[NS], hl[NS], pc[NS];
+      float2 g2[NS][NP];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        A2n[s] = lds32(a2_s + 4 * (n0 + s));
+        cin[s] = lds32(carry_s + 4 * (n0 + s));
+        hl[s] = 0.f;
+        pc[s] = 1.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < TOK / 4; ++kk) {                         // 16-byte pieces of the tile rows, logical order
+        const int k = REV ? TOK / 4 - 1 - kk : kk;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float4 bq = lds128(tile_s + (n0 + s) * (CH * 4) + poff[k]);
+          float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!STATE_ONLY) cq = lds128(tile_s + (N + n0 + s) * (CH * 4) + poff[k]);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int half = REV ? 1 - jj : jj;                      // pair inside the piece, logical order
+            const int j = 2 * k + half;
+            const float2 bp = half ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y);
+            const float2 av = ex2_2(mul2(dt2[j], splat(A2n[s])));
+            const float2 bv = mul2(du2[j], bp);
+            float2 hp, pp;
+            if (REV) {
+              hl[s] = fmaf(av.y, hl[s], bv.y); hp.y = hl[s]; pc[s] *= av.y; pp.y = pc[s];
+              hl[s] = fmaf(av.x, hl[s], bv.x); hp.x = hl[s]; pc[s] *= av.x; pp.x = pc[s];
+            } else {
+              hl[s] = fmaf(av.x, hl[s], bv.x); hp.x = hl[s]; pc[s] *= av.x; pp.x = pc[s];
+              hl[s] = fmaf(av.y, hl[s], bv.y); hp.y = hl[s]; pc[s] *= av.y; pp.y = pc[s];
+            }
+            if (!STATE_ONLY) {
+              const float2 cp = half ? make_float2(cq.z, cq.w) : make_float2(cq.x, cq.y);
+              y2[j] = fma2(cp, hp, y2[j]);
+              g2[s][j] = mul2(cp, pp);
+            }
+          }
+        }
+      }
+      float P[NS], h[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        P[s] = pc[s];
+        if (lane == 0) hl[s] = fmaf(pc[s], cin[s], hl[s]);           // the chunk's carry-in enters through lane 0's aggregate
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) scan_step_up<1>(P[s], hl[s], lane);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) scan_step_up<2>(P[s], hl[s], lane);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) scan_step_up<4>(P[s], hl[s], lane);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) scan_step_up<8>(P[s], hl[s], lane);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) scan_step_up<16>(P[s], hl[s], lane);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        h[s] = __shfl_up_sync(0xffffffffu, hl[s], 1);
+        if (lane == 0) h[s] = cin[s];
+        if (lane == 31) sts32(carry_s + 4 * (n0 + s), hl[s]);        // state at the end of this chunk
+      }
+      if (!STATE_ONLY) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int j = 0; j < NP; ++j) y2[j] = fma2(g2[s][j], splat(h[s]), y2[j]);
+      }
+    };
+    if constexpr (PK == 3) {
+#pragma unroll 1
+      for (int n = 0; n < N; ++n) run_states_pc(n, std::integral_constant<int, 1>{});
+    } else if constexpr (PK == 4) {
+#pragma unroll 1
+      for (int n = 0; n < N; n += 2) run_states_pc(n, std::integral_constant<int, 2>{});
+    } else if constexpr (PK == 1) {
 #pragma unroll 1
       for (int n = 0; n < N; ++n) {
         float2 av2[NP];
@@ -525,7 +610,7 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
               "cad_bimamba_scan_fwd: xz/delta/bc/out must be 16-byte aligned");
   CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CAD_REQUIRE(a->variant == 0 || (a->variant >= 3 && a->variant <= 6), "cad_bimamba_scan_fwd: variant must be 0 or 3..6");
+  CAD_REQUIRE(a->variant == 0 || (a->variant >= 3 && a->variant <= 8), "cad_bimamba_scan_fwd: variant must be 0 or 3..8");
   if (a->variant == 4) {
     CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
                 "halo / h0 / hlast / dtsum / chunk_state / state_only");
@@ -562,6 +647,8 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   CAD_REQUIRE(tok == 16 || tok == 8, "cad_bimamba_scan_fwd: tokens_per_lane must be 0, 8 or 16");
   if (a->chunk_state || a->io_dtype == CAD_F32) tok = 16;
   if (tok == 16 && a->variant == 5) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 1>(*a, G, stream)); }
+  if (tok == 16 && a->variant == 7) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 3>(*a, G, stream)); }
+  if (tok == 16 && a->variant == 8) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 4>(*a, G, stream)); }
   if (tok == 16 && a->variant == 6) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 2>(*a, G, stream)); }
   if (tok == 16) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16>(*a, G, stream)); }
   else if (a->io_dtype == CAD_BF16) return launch_scan<__nv_bfloat16, 16, 8>(*a, G, stream);
