@@ -27,8 +27,6 @@
 //   sum(dt) only, no output), REV/TAIL specialisations (reversed jobs; the one chunk that straddles the sequence end).
 //   profiles: profiles/r1_v1_scan_ncu_summary.txt (v1: 20.8 warp-instructions per element, 43 % issue utilisation)
 //   -> profiles/r1_v3_scan_and_bwd_ncu_summary.txt (11.4 instructions per element, MUFU pipe 53 %, issue 57 %).
-#include <type_traits>
-
 #include "scan_common.cuh"
 #include "scan_fwd_v4.cuh"
 
@@ -49,9 +47,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // One chunk of one channel.  TAIL: the chunk straddles the sequence end (per-token masks, halo in the pad).
-// PK: 0 = scalar fp32 state loop; 1 = token pairs packed (FMUL2 for dt*A2 and du*B, FFMA2 for the C.h accumulation —
-// adjacent PHYSICAL tokens of the lane's segment sit in aligned register pairs, the scalar A2 is the broadcast operand);
-// 2 = 1 + the exp2 of state n+1 issued behind state n's FMA chains and shuffles (two `a` buffers, loop unrolled by 2).
+// PK: 0 = scalar fp32 state loop with a replay pass (variant 3, the default); 3 = packed token pairs, no replay (variant 7).
 template <typename T, int N, int TOK, bool REV, bool TAIL, bool STATE_ONLY, int PK>
 __device__ __forceinline__ void scan_chunk(
     const cad_scan_fwd_args& a, const ScanSmem& sm, int lane, int seg, const uint32_t (&poff)[TOK / 4],
@@ -128,19 +124,6 @@ __device__ __forceinline__ void scan_chunk(
 
   // ---- 3. the scan, one state at a time, on the TMA-staged B/C tile ------------------------------------
   mbar_wait(sm.bar, parity);
-  if (a.stagger > 0) {
-    // De-phase the warps that share a scheduler.  Every warp's state iteration is a MUFU burst (16 exp2) followed by
-    // ~300 cycles of dependent FMA / shuffle latency; warps that start a chunk together stay in lock-step (the MUFU
-    // pipe interleaves their bursts fairly), so the pipe idles while ALL of them sit in the latency phase.  Holding
-    // every second warp of a scheduler back by about half an iteration lets one group's bursts fill the other's gaps.
-    const int w = threadIdx.x >> 5;
-    const int mode = a.stagger >> 16, cyc = a.stagger & 0xffff;
-    const int grp = mode == 0 ? ((w >> 2) & 1) : (mode == 1 ? (w & 1) : (w % 3));
-    if (grp) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)cyc * grp) {}
-    }
-  }
   const uint32_t tile_s = smem_u32(sm.tile);
   const uint32_t a2_s = smem_u32(my_a2), carry_s = smem_u32(my_carry);
   if constexpr (PK == 0) {
@@ -196,6 +179,14 @@ __device__ __forceinline__ void scan_chunk(
       }
     }
   } else {
+    // PK 3 — token pairs packed, no replay pass.  Adjacent PHYSICAL tokens of the lane's segment sit in aligned
+    // register pairs (FMUL2 / FFMA2 with the scalar A2 or carry as the broadcast operand).  The zero-state pass also
+    // accumulates y += C.h_local and the running decay pc_t = prod_{s<=t} a_s; after the warp scan the carry-in enters
+    // as 8 INDEPENDENT packed FMAs  y_t += (C_t pc_t) * h_in.  Against the replay form this drops the second 16-step
+    // dependent chain, the stored a / b arrays (32 registers) and the extra exp2 of the segment decay (the aggregate
+    // IS pc_15); it adds one FMUL (pc) and half a packed FMUL (C*pc) per element.  127 instead of 137 instructions
+    // per (lane, state); measured equal to PK 0 on Caduceus-PS and 5 % faster on Caduceus-Ph
+    // (profiles/r1_ab_scan_v3_v7_v8.jsonl) — the loop is bound by MUFU / shuffle latency, not by issue slots.
     using v4::fma2; using v4::mul2; using v4::splat; using v4::ex2_2;
     constexpr int NP = TOK / 2;
     auto lgc = [](int p) { return REV ? TOK - 1 - p : p; };          // physical token of the segment -> logical item
@@ -206,33 +197,42 @@ __device__ __forceinline__ void scan_chunk(
       du2[j] = make_float2(du[lgc(2 * j)], du[lgc(2 * j + 1)]);
       y2[j] = make_float2(y[lgc(2 * j)], y[lgc(2 * j + 1)]);
     }
-    auto compute_a = [&](int n, float2 (&av2)[NP]) {
-      const float A2n = lds32(a2_s + 4 * n);
-#pragma unroll
-      for (int j = 0; j < NP; ++j) av2[j] = ex2_2(mul2(dt2[j], splat(A2n)));
-    };
-    auto run_state = [&](int n, const float2 (&av2)[NP]) {
+#pragma unroll 1
+    for (int n = 0; n < N; ++n) {
       const float A2n = lds32(a2_s + 4 * n);
       const float cin = lds32(carry_s + 4 * n);
-      float2 bv2[NP];
-      float hl = (lane == 0) ? cin : 0.f;
-      {
-        const uint32_t rowp = tile_s + n * (CH * 4);
+      float hl = 0.f, pc = 1.f;
+      float2 g2[NP];
 #pragma unroll
-        for (int k = 0; k < TOK / 4; ++k) {
-          const float4 q = lds128(rowp + poff[k]);
-          bv2[2 * k] = mul2(du2[2 * k], make_float2(q.x, q.y));
-          bv2[2 * k + 1] = mul2(du2[2 * k + 1], make_float2(q.z, q.w));
-        }
+      for (int kk = 0; kk < TOK / 4; ++kk) {                         // 16-byte pieces of the tile rows, logical order
+        const int k = REV ? TOK / 4 - 1 - kk : kk;
+        const float4 bq = lds128(tile_s + n * (CH * 4) + poff[k]);
+        float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!STATE_ONLY) cq = lds128(tile_s + (N + n) * (CH * 4) + poff[k]);
 #pragma unroll
-        for (int i = 0; i < TOK; ++i) {                              // logical order
-          const int p = REV ? TOK - 1 - i : i;
-          const float aa = (p & 1) ? av2[p >> 1].y : av2[p >> 1].x;
-          const float bb = (p & 1) ? bv2[p >> 1].y : bv2[p >> 1].x;
-          hl = fmaf(aa, hl, bb);
+        for (int jj = 0; jj < 2; ++jj) {
+          const int half = REV ? 1 - jj : jj;                        // pair inside the piece, logical order
+          const int j = 2 * k + half;
+          const float2 bp = half ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y);
+          const float2 av = ex2_2(mul2(dt2[j], splat(A2n)));
+          const float2 bv = mul2(du2[j], bp);
+          float2 hp, pp;
+          if (REV) {
+            hl = fmaf(av.y, hl, bv.y); hp.y = hl; pc *= av.y; pp.y = pc;
+            hl = fmaf(av.x, hl, bv.x); hp.x = hl; pc *= av.x; pp.x = pc;
+          } else {
+            hl = fmaf(av.x, hl, bv.x); hp.x = hl; pc *= av.x; pp.x = pc;
+            hl = fmaf(av.y, hl, bv.y); hp.y = hl; pc *= av.y; pp.y = pc;
+          }
+          if (!STATE_ONLY) {
+            const float2 cp = half ? make_float2(cq.z, cq.w) : make_float2(cq.x, cq.y);
+            y2[j] = fma2(cp, hp, y2[j]);
+            g2[j] = mul2(cp, pp);
+          }
         }
       }
-      float P = ex2(A2n * dsum);
+      float P = pc;
+      if (lane == 0) hl = fmaf(pc, cin, hl);                         // the chunk's carry-in enters through lane 0's aggregate
       scan_step_up<1>(P, hl, lane);
       scan_step_up<2>(P, hl, lane);
       scan_step_up<4>(P, hl, lane);
@@ -240,128 +240,10 @@ __device__ __forceinline__ void scan_chunk(
       scan_step_up<16>(P, hl, lane);
       float h = __shfl_up_sync(0xffffffffu, hl, 1);
       if (lane == 0) h = cin;
-      if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
-      if (!STATE_ONLY) {
-        const uint32_t rowp = tile_s + (N + n) * (CH * 4);
-        float4 cq[TOK / 4];
-#pragma unroll
-        for (int k = 0; k < TOK / 4; ++k) cq[k] = lds128(rowp + poff[k]);
-#pragma unroll
-        for (int jj = 0; jj < NP; ++jj) {                            // pairs in logical order
-          const int j = REV ? NP - 1 - jj : jj;
-          float2 hp;
-          if (REV) {
-            h = fmaf(av2[j].y, h, bv2[j].y); hp.y = h;
-            h = fmaf(av2[j].x, h, bv2[j].x); hp.x = h;
-          } else {
-            h = fmaf(av2[j].x, h, bv2[j].x); hp.x = h;
-            h = fmaf(av2[j].y, h, bv2[j].y); hp.y = h;
-          }
-          const float4 c4 = cq[j >> 1];
-          const float2 cp = (j & 1) ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
-          y2[j] = fma2(cp, hp, y2[j]);
-        }
-      }
-    };
-    // PK 3 / 4 — no replay: the zero-state pass also accumulates y += C.h_local and the running decay
-    // pc_t = prod_{s<=t} a_s; after the warp scan the carry-in enters as 8 INDEPENDENT packed FMAs
-    // y_t += (C_t pc_t) * h_in.  Against the replay form this drops the second 16-step dependent chain, the stored
-    // a / b arrays (32 registers) and the extra exp2 of the segment decay (the aggregate IS pc_15); it adds one FMUL
-    // (pc) and half a packed FMUL (C*pc) per element, issued in the MUFU-bound phase where issue slots are idle.
-    // NS = 2 (PK 4) runs two states side by side so that their shuffle rounds overlap.
-    auto run_states_pc = [&](int n0, auto ns_tag) {
-      constexpr int NS = decltype(ns_tag)::value;
-      float A2n[NS], cin[NS], hl[NS], pc[NS];
-      float2 g2[NS][NP];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        A2n[s] = lds32(a2_s + 4 * (n0 + s));
-        cin[s] = lds32(carry_s + 4 * (n0 + s));
-        hl[s] = 0.f;
-        pc[s] = 1.f;
-      }
-#pragma unroll
-      for (int kk = 0; kk < TOK / 4; ++kk) {                         // 16-byte pieces of the tile rows, logical order
-        const int k = REV ? TOK / 4 - 1 - kk : kk;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const float4 bq = lds128(tile_s + (n0 + s) * (CH * 4) + poff[k]);
-          float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!STATE_ONLY) cq = lds128(tile_s + (N + n0 + s) * (CH * 4) + poff[k]);
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int half = REV ? 1 - jj : jj;                      // pair inside the piece, logical order
-            const int j = 2 * k + half;
-            const float2 bp = half ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y);
-            const float2 av = ex2_2(mul2(dt2[j], splat(A2n[s])));
-            const float2 bv = mul2(du2[j], bp);
-            float2 hp, pp;
-            if (REV) {
-              hl[s] = fmaf(av.y, hl[s], bv.y); hp.y = hl[s]; pc[s] *= av.y; pp.y = pc[s];
-              hl[s] = fmaf(av.x, hl[s], bv.x); hp.x = hl[s]; pc[s] *= av.x; pp.x = pc[s];
-            } else {
-              hl[s] = fmaf(av.x, hl[s], bv.x); hp.x = hl[s]; pc[s] *= av.x; pp.x = pc[s];
-              hl[s] = fmaf(av.y, hl[s], bv.y); hp.y = hl[s]; pc[s] *= av.y; pp.y = pc[s];
-            }
-            if (!STATE_ONLY) {
-              const float2 cp = half ? make_float2(cq.z, cq.w) : make_float2(cq.x, cq.y);
-              y2[j] = fma2(cp, hp, y2[j]);
-              g2[s][j] = mul2(cp, pp);
-            }
-          }
-        }
-      }
-      float P[NS], h[NS];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        P[s] = pc[s];
-        if (lane == 0) hl[s] = fmaf(pc[s], cin[s], hl[s]);           // the chunk's carry-in enters through lane 0's aggregate
-      }
-#pragma unroll
-      for (int s = 0; s < NS; ++s) scan_step_up<1>(P[s], hl[s], lane);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) scan_step_up<2>(P[s], hl[s], lane);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) scan_step_up<4>(P[s], hl[s], lane);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) scan_step_up<8>(P[s], hl[s], lane);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) scan_step_up<16>(P[s], hl[s], lane);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        h[s] = __shfl_up_sync(0xffffffffu, hl[s], 1);
-        if (lane == 0) h[s] = cin[s];
-        if (lane == 31) sts32(carry_s + 4 * (n0 + s), hl[s]);        // state at the end of this chunk
-      }
+      if (lane == 31) sts32(carry_s + 4 * n, hl);                    // state at the end of this chunk
       if (!STATE_ONLY) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
-#pragma unroll
-          for (int j = 0; j < NP; ++j) y2[j] = fma2(g2[s][j], splat(h[s]), y2[j]);
-      }
-    };
-    if constexpr (PK == 3) {
-#pragma unroll 1
-      for (int n = 0; n < N; ++n) run_states_pc(n, std::integral_constant<int, 1>{});
-    } else if constexpr (PK == 4) {
-#pragma unroll 1
-      for (int n = 0; n < N; n += 2) run_states_pc(n, std::integral_constant<int, 2>{});
-    } else if constexpr (PK == 1) {
-#pragma unroll 1
-      for (int n = 0; n < N; ++n) {
-        float2 av2[NP];
-        compute_a(n, av2);
-        run_state(n, av2);
-      }
-    } else {
-      float2 avA[NP], avB[NP];
-      compute_a(0, avA);
-#pragma unroll 1
-      for (int n = 0; n < N; n += 2) {
-        compute_a(n + 1, avB);
-        run_state(n, avA);
-        if (n + 2 < N) compute_a(n + 2, avA);
-        run_state(n + 1, avB);
+        for (int j = 0; j < NP; ++j) y2[j] = fma2(g2[j], splat(h), y2[j]);
       }
     }
 #pragma unroll
@@ -533,13 +415,6 @@ bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUten
   scan_kernel_body<T, N, TOK, STATE_ONLY, PK>(a, &tmap);
 }
 
-// PK = 2 keeps two `a` buffers live: 144 registers (14 warps x 32 x 144 = 64512 <= 65536, still 2 CTAs per SM)
-template <typename T, int N, bool STATE_ONLY>
-__global__ void __maxnreg__(144)
-bimamba_scan_fwd_pipe_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
-  scan_kernel_body<T, N, 16, STATE_ONLY, 2>(a, &tmap);
-}
-
 template <typename T, int N, int TOK, int PK = 0>
 static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
   constexpr int CH = 32 * TOK;
@@ -548,11 +423,7 @@ static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
 
   const size_t pre_bytes = sizeof(T) == 2 ? (size_t)2 * G * 3 * CH * sizeof(T) : 0;
   const size_t smem = 1024 + (size_t)2 * N * CH * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16 + pre_bytes;
-  void (*kern)(const cad_scan_fwd_args, const CUtensorMap);
-  if constexpr (PK == 2 && TOK == 16)
-    kern = a.state_only ? bimamba_scan_fwd_pipe_kernel<T, N, true> : bimamba_scan_fwd_pipe_kernel<T, N, false>;
-  else
-    kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, TOK, true, PK> : bimamba_scan_fwd_kernel<T, N, TOK, false, PK>;
+  auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, TOK, true, PK> : bimamba_scan_fwd_kernel<T, N, TOK, false, PK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
@@ -610,7 +481,8 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
               "cad_bimamba_scan_fwd: xz/delta/bc/out must be 16-byte aligned");
   CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CAD_REQUIRE(a->variant == 0 || (a->variant >= 3 && a->variant <= 8), "cad_bimamba_scan_fwd: variant must be 0 or 3..8");
+  CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4 || a->variant == 7,
+              "cad_bimamba_scan_fwd: variant must be 0, 3, 4 or 7");
   if (a->variant == 4) {
     CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
                 "halo / h0 / hlast / dtsum / chunk_state / state_only");
@@ -646,10 +518,7 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   if (tok == 0) tok = 16;
   CAD_REQUIRE(tok == 16 || tok == 8, "cad_bimamba_scan_fwd: tokens_per_lane must be 0, 8 or 16");
   if (a->chunk_state || a->io_dtype == CAD_F32) tok = 16;
-  if (tok == 16 && a->variant == 5) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 1>(*a, G, stream)); }
   if (tok == 16 && a->variant == 7) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 3>(*a, G, stream)); }
-  if (tok == 16 && a->variant == 8) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 4>(*a, G, stream)); }
-  if (tok == 16 && a->variant == 6) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 2>(*a, G, stream)); }
   if (tok == 16) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16>(*a, G, stream)); }
   else if (a->io_dtype == CAD_BF16) return launch_scan<__nv_bfloat16, 16, 8>(*a, G, stream);
   else return launch_scan<__half, 16, 8>(*a, G, stream);

@@ -145,14 +145,11 @@ typedef struct {
   int32_t channels_per_cta; /* 0 = library picks so that the grid is ~ a multiple of the SM count */
   int32_t state_only;       /* 1: only hlast / dtsum are produced (pass 1 of a sequence-sharded scan); out may be NULL */
   int32_t tokens_per_lane;  /* 0 = default (16); 8 = 256-token chunks with more CTAs per SM (16-bit I/O, no chunk_state) */
-  int32_t variant;          /* 0 = library default; 3 = one channel per warp, scalar fp32 state loop; 5 = 3 with token
-                               pairs packed (FMUL2 / FFMA2); 6 = 5 with the exp2 of the next state software-pipelined
-                               (144 registers); 4 = two channels per warp with packed fp32 (inference only: 16-bit I/O,
-                               even E, no sharding hooks / saved states — an error otherwise; channels_per_cta then
-                               counts channel PAIRS).  Variants 5 / 6 apply to 16 tokens per lane. */
-  int32_t stagger;          /* variants 3 / 5 / 6: 0 = off; else bits 0-15 = cycles by which every second warp of a
-                               scheduler is held back at the start of each chunk's state loop, bits 16-17 = grouping
-                               (0: (warp >> 2) & 1, 1: warp & 1, 2: warp % 3 with 1x / 2x the delay) */
+  int32_t variant;          /* 0 = library default (3); 3 = one channel per warp, scalar fp32 state loop with a replay
+                               pass; 7 = 3 with token pairs packed (FMUL2 / FFMA2) and no replay pass (16 tokens per
+                               lane); 4 = two channels per warp with packed fp32 (inference only: 16-bit I/O, even E,
+                               no sharding hooks / saved states — an error otherwise; channels_per_cta then counts
+                               channel PAIRS) */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */

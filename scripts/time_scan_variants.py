@@ -17,8 +17,7 @@ ap.add_argument("--model", default="ps", help="ps, ph or ps,ph")
 ap.add_argument("--L", type=int, default=131072)
 ap.add_argument("--E", type=int, default=512)
 ap.add_argument("--iters", type=int, default=10)
-ap.add_argument("--variants", default="3,4")
-ap.add_argument("--staggers", default="0", help="comma list of cad_scan_fwd_args.stagger values tried for variants 3/5/6")
+ap.add_argument("--variants", default="3,7,4")
 args = ap.parse_args()
 
 dev = "cuda"
@@ -50,18 +49,16 @@ for model in args.model.split(","):
     jobs = (seq, pset, rev)
 
     base = None
-    combos = [(int(v), int(st)) for v in args.variants.split(",") for st in args.staggers.split(",")
-              if int(st) == 0 or int(v) in (3, 5, 6)]
-    for v, stg in combos:
+    for v in [int(s) for s in args.variants.split(",")]:
         try:
             out = None
             for _ in range(3):
-                out, _, _, _ = CF.scan_fwd(*sets[0], packed, jobs, L, variant=v, stagger=stg)
+                out, _, _, _ = CF.scan_fwd(*sets[0], packed, jobs, L, variant=v)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(args.iters):
-                CF.scan_fwd(*sets[i & 1], packed, jobs, L, variant=v, stagger=stg)
+                CF.scan_fwd(*sets[i & 1], packed, jobs, L, variant=v)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
@@ -69,7 +66,7 @@ for model in args.model.split(","):
             if base is None:
                 base = o
             nt_calls = nstrand * L
-            print(json.dumps({"variant": v, "stagger": stg, "model": model, "L": L, "E": E, "ms_per_launch": round(ms, 4),
+            print(json.dumps({"variant": v, "model": model, "L": L, "E": E, "ms_per_launch": round(ms, 4),
                               "boundary_S_GBps": round(8320 * nt_calls / ms / 1e6, 1),
                               "finite": bool(torch.isfinite(o).all()), "max_abs": float(o.abs().max()),
                               "max_abs_diff_vs_first": float((o - base).abs().max())}), flush=True)

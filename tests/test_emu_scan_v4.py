@@ -107,7 +107,7 @@ def _run_emu(lib, L, E, spec, dtype, G, seed):
     a = _lib.ScanFwdArgs(p(xz), p(delta), p(bc), p(out), p(conv_w4), p(conv_b), p(dt_b), p(A2), p(Dk),
                          p(tabs[0]), p(tabs[1]), p(tabs[2]), None, None, None, None, None,
                          L, E, 16, 4, ld, ld, ldbc, ld, xz.shape[0], njobs, conv_w4.shape[0],
-                         _lib.CAD_BF16 if dtype == torch.bfloat16 else _lib.CAD_F16, G, 0, 0, 4, 0)
+                         _lib.CAD_BF16 if dtype == torch.bfloat16 else _lib.CAD_F16, G, 0, 0, 4)
     assert lib.emu_scan_v4(C.byref(a), G) == 0
     f = lambda t: t.float().numpy()   # noqa: E731
     ref = boundary_ref(f(xz), f(delta), f(bc), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk),

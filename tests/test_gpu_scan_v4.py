@@ -63,6 +63,33 @@ def test_v4_agrees_with_v3_on_identical_inputs():
     assert np.abs(g4 - g3).max() <= 2e-3 + 2.0 ** -6 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("L", [1, 17, 513, 2300])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_v7_no_replay_variant_vs_boundary_restatement(L, rev):
+    """variant 7 (packed token pairs, no replay pass) on the same checker as v4."""
+    got, ref = _run(L, 64, [(0, 0, rev)], torch.bfloat16, 0, 200 + L, 7)
+    _check(got, ref, torch.bfloat16, f"v7 L={L} rev={rev}")
+
+
+def test_v7_state_outputs_match_v3_fp32():
+    """fp32 I/O, carry-in, end state, sum(dt) and the saved chunk states (the training / sharding hooks) must agree
+    between the replay form (3) and the no-replay form (7): same recurrence, different association of the carry term."""
+    from caduceus_b200 import functional as CF
+    L, E = 1700, 48
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, [(0, 0, 0), (0, 1, 1)], torch.float32, 5)
+    d = lambda t: t.to(DEV).contiguous()   # noqa: E731
+    h0 = torch.randn(2, E, 16, device=DEV)
+    outs = {}
+    for v in (3, 7):
+        outs[v] = CF.scan_fwd(d(xz), d(delta), d(bc), tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)),
+                              tuple(d(t) for t in tabs), L, h0=h0, want_state=True, want_chunk_state=True, variant=v)
+    for got, ref, what in zip(outs[7], outs[3], ("out", "hlast", "dtsum", "chunk_state")):
+        got, ref = got.float().cpu(), ref.float().cpu()
+        if what == "out":
+            got, ref = got[..., :L], ref[..., :L]
+        assert torch.allclose(got, ref, rtol=2e-4, atol=2e-4 * float(ref.abs().max())), (what, (got - ref).abs().max())
+
+
 def test_v4_rejects_what_it_does_not_cover():
     from caduceus_b200 import functional as CF
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(100, 8, [(0, 0, 0)], torch.float32, 0)
