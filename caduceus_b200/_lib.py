@@ -52,7 +52,8 @@ class ScanFwdArgs(C.Structure):
                 ("L", _i64), ("E", _i64), ("N", _i64), ("K", _i64),
                 ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
                 ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
-                ("state_only", _i32), ("tokens_per_lane", _i32), ("variant", _i32)]
+                ("state_only", _i32), ("tokens_per_lane", _i32), ("variant", _i32),
+                ("bc16", _p), ("ldbc16", _i64)]
 
 
 class ScanFixupArgs(C.Structure):

@@ -118,4 +118,23 @@ inline int make_row_tile_map(CUtensorMap* tmap, const float* base, int64_t nrows
   return 0;
 }
 
+
+// same for a 16-bit (nrows, ld) matrix viewed as (64 tokens, blocks, rows): a 128-byte swizzle line holds 64 tokens
+inline int make_row_tile_map16(CUtensorMap* tmap, const void* base, int is_bf16, int64_t nrows, int64_t ld, int64_t L,
+                               int rows_per_box, int chunk_tokens) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return -1; }
+  constexpr int kLine = 64;
+  const cuuint64_t nblk = (cuuint64_t)((L + kLine - 1) / kLine);
+  const cuuint64_t dims[3] = {(cuuint64_t)kLine, nblk, (cuuint64_t)nrows};
+  const cuuint64_t strides[2] = {(cuuint64_t)kLine * 2, (cuuint64_t)ld * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)kLine, (cuuint32_t)(chunk_tokens / kLine), (cuuint32_t)rows_per_box};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tmap, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (16-bit) failed (%d)", (int)r); return -1; }
+  return 0;
+}
+
 }  // namespace cad

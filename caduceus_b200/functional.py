@@ -15,7 +15,7 @@ _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
 SCAN_TOKENS_PER_LANE = 0   # 0 = library default; 8 / 16 force the scan's tokens per lane (tuning knob)
-SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7: see cad_scan_fwd_args.variant
+SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7 / 9 / 10: see cad_scan_fwd_args.variant
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
 
@@ -287,7 +287,7 @@ def project_dt_bc(xdbl, dt_w_job, L, N):
 
 
 def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
-             channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None):
+             channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None, bc16=None):
     """Launch the fused bidirectional scan.
     xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld)."""
     lib = _lib.load()
@@ -310,8 +310,15 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
         _ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
         L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only),
-        SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0)
+        SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0, None, 0)
     a.variant = scan_variant(a) if variant is None else int(variant)
+    if a.variant in (9, 10):
+        # 16-bit copy of the B / C rows for the 16-bit-tile kernels (experimental path: a cast per call until the
+        # conv_xproj kernel writes it directly); columns [L, ldbc16) must be zero
+        if bc16 is None:
+            bc16 = torch.zeros(njobs, twoN, round_up(L, 64), device=xz.device, dtype=xz.dtype)
+            bc16[..., :L] = bc[..., :L]
+        a.bc16, a.ldbc16 = _ptr(bc16), bc16.stride(1)
     ev = None
     if SCAN_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -331,6 +338,8 @@ def scan_variant(a):
         ok = (a.io_dtype != CAD_F32 and a.N == 16 and a.E % 2 == 0 and not (a.halo or a.h0 or a.hlast or a.dtsum
               or a.chunk_state) and not a.state_only and a.tokens_per_lane in (0, 16))
         return 4 if ok else 0
+    if SCAN_VARIANT in (9, 10):
+        return SCAN_VARIANT if (a.io_dtype != CAD_F32 and a.N == 16 and a.tokens_per_lane in (0, 16)) else 0
     return SCAN_VARIANT
 
 

@@ -147,9 +147,13 @@ typedef struct {
   int32_t tokens_per_lane;  /* 0 = default (16); 8 = 256-token chunks with more CTAs per SM (16-bit I/O, no chunk_state) */
   int32_t variant;          /* 0 = library default (3); 3 = one channel per warp, scalar fp32 state loop with a replay
                                pass; 7 = 3 with token pairs packed (FMUL2 / FFMA2) and no replay pass (16 tokens per
-                               lane); 4 = two channels per warp with packed fp32 (inference only: 16-bit I/O, even E,
-                               no sharding hooks / saved states — an error otherwise; channels_per_cta then counts
-                               channel PAIRS) */
+                               lane); 9 / 10 = 7's state loop on a 16-BIT B/C tile (bc16), two tile buffers handed over
+                               through mbarriers + arrival counters instead of a per-chunk CTA barrier, 10 adds the
+                               exp2 software pipeline (16-bit I/O; all hooks); 4 = two channels per warp with packed
+                               fp32 (inference only: 16-bit I/O, even E, no sharding hooks / saved states — an error
+                               otherwise; channels_per_cta then counts channel PAIRS) */
+  const void* bc16;         /* variants 9 / 10: (njobs, 2N, ldbc16) B / C rows in the I/O dtype, zeros in [L, ldbc16) */
+  int64_t ldbc16;           /* multiple of 64 elements, >= L */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */

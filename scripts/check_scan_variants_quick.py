@@ -5,7 +5,7 @@ import sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
-import test_gpu_scan_v4 as T  # noqa: E402
+import test_gpu_scan_variants as T  # noqa: E402
 
 for L in (17, 513, 2300):
     for rev in (0, 1):

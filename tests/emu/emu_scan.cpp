@@ -1,0 +1,96 @@
+// Host driver of the SIMT emulation of the v4 / v9 scan kernels (TEST INFRASTRUCTURE ONLY; see simt_emu.h).
+//   g++ -O1 -std=c++17 -shared -fPIC -pthread -DCAD_EMULATE -I tests/emu -I $CUDA/include tests/emu/emu_scan.cpp
+// All pointers in cad_scan_fwd_args are HOST pointers here.
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CAD_EMULATE 1
+#include "simt_emu.h"
+#include "../../caduceus_b200/csrc/scan_fwd_v4.cuh"
+#include "../../caduceus_b200/csrc/scan_fwd_v9.cuh"
+
+namespace cad {
+thread_local EmuThread g_t;
+}
+
+template <typename Body>
+static void run_cta(size_t smem_bytes, int G, int bx, int by, Body body) {
+  using namespace cad;
+  EmuCta cta;
+  cta.smem_bytes = smem_bytes;
+  void* mem = nullptr;
+  if (posix_memalign(&mem, 1024, cta.smem_bytes) != 0) abort();
+  memset(mem, 0xCD, cta.smem_bytes);               // poison: reading unstaged shared memory shows up as garbage
+  cta.smem = (unsigned char*)mem;
+  cta.nthreads = G * 32;
+  pthread_barrier_init(&cta.cta_bar, nullptr, cta.nthreads);
+  cta.warp_bar.resize(G);
+  for (int w = 0; w < G; ++w) pthread_barrier_init(&cta.warp_bar[w], nullptr, 32);
+  cta.xchg.assign((size_t)G * 32, 0.f);
+  std::vector<std::thread> th;
+  for (int t = 0; t < cta.nthreads; ++t)
+    th.emplace_back([&, t] {
+      g_t = EmuThread{&cta, t, bx, by};
+      body(cta.smem);
+    });
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&cta.cta_bar);
+  for (int w = 0; w < G; ++w) pthread_barrier_destroy(&cta.warp_bar[w]);
+  free(mem);
+}
+
+extern "C" int emu_scan_v4(const cad_scan_fwd_args* a, int G) {
+  using namespace cad;
+  if (a->N != v4::NST || a->E % 2 || G < 1 || G > v4::kMaxG4 || a->io_dtype == CAD_F32) return -1;
+  if (a->L <= 0) return 0;
+  EmuTmap tmap;
+  tmap.base = a->bc;
+  tmap.nrows = (int64_t)a->njobs * 2 * v4::NST;
+  tmap.ld = a->ldbc;
+  tmap.nblk = (a->L + 31) / 32;
+  tmap.box_blocks = v4::CH / 32;
+  tmap.box_rows = 2 * v4::NST;
+  const int gx = (int)((a->E / 2 + G - 1) / G);
+  for (int by = 0; by < a->njobs; ++by)
+    for (int bx = 0; bx < gx; ++bx) {
+      if (a->io_dtype == CAD_BF16)
+        run_cta(v4::smem_bytes(G, 2), G, bx, by, [&](unsigned char* sm) { v4::kernel_body<__nv_bfloat16>(*a, &tmap, sm); });
+      else
+        run_cta(v4::smem_bytes(G, 2), G, bx, by, [&](unsigned char* sm) { v4::kernel_body<__half>(*a, &tmap, sm); });
+    }
+  return 0;
+}
+
+template <typename T>
+static void run_v9(const cad_scan_fwd_args* a, const cad::EmuTmap* tmap, int G, int bx, int by, int pipe) {
+  using namespace cad;
+  const size_t sb = v9::smem_bytes(G, sizeof(T));
+  if (a->state_only) {
+    if (pipe) run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, true, true>(*a, tmap, sm); });
+    else      run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, true, false>(*a, tmap, sm); });
+  } else {
+    if (pipe) run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, false, true>(*a, tmap, sm); });
+    else      run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, false, false>(*a, tmap, sm); });
+  }
+}
+
+extern "C" int emu_scan_v9(const cad_scan_fwd_args* a, int G, int pipe) {
+  using namespace cad;
+  if (a->N != v9::NST || G < 1 || G > v9::kMaxG9 || a->io_dtype == CAD_F32 || !a->bc16 || a->ldbc16 % 64) return -1;
+  if (a->L <= 0) return 0;
+  EmuTmap tmap;
+  tmap.base = a->bc16;
+  tmap.elem_bytes = 2;
+  tmap.nrows = (int64_t)a->njobs * 2 * v9::NST;
+  tmap.ld = a->ldbc16;
+  tmap.nblk = (a->L + 63) / 64;
+  tmap.box_blocks = v9::CH / 64;
+  tmap.box_rows = 2 * v9::NST;
+  const int gx = (int)((a->E + G - 1) / G);
+  for (int by = 0; by < a->njobs; ++by)
+    for (int bx = 0; bx < gx; ++bx) {
+      if (a->io_dtype == CAD_BF16) run_v9<__nv_bfloat16>(a, &tmap, G, bx, by, pipe);
+      else run_v9<__half>(a, &tmap, G, bx, by, pipe);
+    }
+  return 0;
+}

@@ -43,10 +43,11 @@ template <> struct io<__nv_bfloat16> {
   static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
 };
 
-struct EmuTmap {              // (32 tokens, blocks, rows) view of an fp32 (nrows, ld) matrix, as make_row_tile_map
-  const float* base;
-  int64_t nrows, ld, nblk;    // nblk = ceil(L / 32)
+struct EmuTmap {              // (128-byte line, blocks, rows) view of an (nrows, ld) matrix, as make_row_tile_map[16]
+  const void* base;
+  int64_t nrows, ld, nblk;    // ld in elements; nblk = ceil(L / tokens per line)
   int box_blocks, box_rows;
+  int elem_bytes = 4;         // 4: 32 tokens per line; 2: 64 tokens per line
 };
 
 struct Mbar { int init = 0, pending = 0; long tx = 0; uint32_t phase = 0; };
@@ -117,21 +118,39 @@ inline void tma_load_3d(void* smem_dst, const EmuTmap* t, int c0, int c1, int c2
   if (c0 != 0 || (smem_u32(smem_dst) & 1023)) { fprintf(stderr, "emu: bad TMA destination / coordinate\n"); abort(); }
   unsigned char* dst = (unsigned char*)smem_dst;
   smem_at(smem_u32(smem_dst), (size_t)t->box_rows * t->box_blocks * 128);
+  const int eb = t->elem_bytes, per_line = 128 / eb, per_piece = 16 / eb;
   for (int r = 0; r < t->box_rows; ++r)
     for (int b = 0; b < t->box_blocks; ++b) {
       const int line = r * t->box_blocks + b;
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < per_line; ++j) {
         const int64_t row = (int64_t)c2 + r, blk = (int64_t)c1 + b;
-        float v = 0.f;
-        if (row >= 0 && row < t->nrows && blk >= 0 && blk < t->nblk) v = t->base[row * t->ld + blk * 32 + j];
-        const int chunk = (j >> 2) ^ (line & 7);
-        memcpy(dst + (size_t)line * 128 + chunk * 16 + (j & 3) * 4, &v, 4);
+        unsigned char v[4] = {0, 0, 0, 0};
+        if (row >= 0 && row < t->nrows && blk >= 0 && blk < t->nblk)
+          memcpy(v, (const unsigned char*)t->base + ((size_t)row * t->ld + (size_t)blk * per_line + j) * eb, eb);
+        const int chunk = (j / per_piece) ^ (line & 7);
+        memcpy(dst + (size_t)line * 128 + chunk * 16 + (j % per_piece) * eb, v, eb);
       }
     }
   std::lock_guard<std::mutex> g(g_t.cta->m);
   Mbar& mb = g_t.cta->mbars.at(bar);
   mb.tx -= (long)t->box_rows * t->box_blocks * 128;
   mbar_complete_locked(mb);
+}
+
+// ---- math of common.cuh (exact libm in place of the MUFU approximations) ----------------------------------------
+inline float rcp(float x) { return 1.0f / x; }
+inline float silu(float v) { return v * rcp(1.0f + ex2(-kLog2e * v)); }
+template <typename T>
+inline float silu_io(float v) {
+  if (sizeof(T) == 2) { const float h = 0.5f * v; return fmaf(h, tanh_approx(h), h); }
+  return silu(v);
+}
+inline float softplus(float v) {
+  const float w = ex2(kLog2e * v);
+  float sp = kLn2 * lg2(1.0f + w);
+  const float series = w * (1.0f - w * (0.5f - w * (0.33333334f - 0.25f * w)));
+  sp = (w < 0.015625f) ? series : sp;
+  return v > 20.0f ? v : sp;
 }
 
 template <int TOK_>
@@ -182,4 +201,24 @@ inline void scan_step_up2(float2& P, float2& H, int lane) {
   }
 }
 }  // namespace v4
+
+namespace v9 {
+inline uint32_t atomic_inc_shared(uint32_t a) {
+  std::lock_guard<std::mutex> g(g_t.cta->m);
+  uint32_t old; memcpy(&old, smem_at(a, 4), 4);
+  const uint32_t nw = old + 1; memcpy(smem_at(a, 4), &nw, 4);
+  return old;
+}
+inline void sts32u(uint32_t a, uint32_t v) { if (a & 3) abort(); std::lock_guard<std::mutex> g(g_t.cta->m); memcpy(smem_at(a, 4), &v, 4); }
+inline void warp_sync() { pthread_barrier_wait(&g_t.cta->warp_bar[g_t.tid >> 5]); }
+inline float shfl_up1(float v, int off) { return v4::shfl_up1(v, off); }
+inline float shfl_idx1(float v, int src) { return v4::shfl_raw(v, src); }
+inline float shfl_xor1(float v, int m) { return v4::shfl_raw(v, (g_t.tid & 31) ^ m); }
+template <int OFF>
+inline void scan_step1(float& P, float& H, int lane) {
+  const float Pp = shfl_up1(P, OFF), Hp = shfl_up1(H, OFF);
+  if (lane >= OFF) { H = fmaf(P, Hp, H); P = P * Pp; }
+}
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+}  // namespace v9
 }  // namespace cad

@@ -18,14 +18,15 @@ from caduceus_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
-EMU_SO = os.path.join(EMU_DIR, "libemu_scan_v4.so")
+EMU_SO = os.path.join(EMU_DIR, "libemu_scan.so")
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
 
 
 @pytest.fixture(scope="module")
 def emu():
-    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_scan_v4.cpp", "simt_emu.h")] + [
-        os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fwd_v4.cuh"), os.path.join(ROOT, "include", "caduceus_b200.h")]
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_scan.cpp", "simt_emu.h")] + [
+        os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fwd_v4.cuh"),
+        os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fwd_v9.cuh"), os.path.join(ROOT, "include", "caduceus_b200.h")]
     if not os.path.exists(os.path.join(CUDA_INC, "cuda_bf16.h")):
         pytest.skip("CUDA headers not found")
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
@@ -34,69 +35,12 @@ def emu():
     lib = C.CDLL(EMU_SO)
     lib.emu_scan_v4.restype = C.c_int
     lib.emu_scan_v4.argtypes = [C.POINTER(_lib.ScanFwdArgs), C.c_int]
+    lib.emu_scan_v9.restype = C.c_int
+    lib.emu_scan_v9.argtypes = [C.POINTER(_lib.ScanFwdArgs), C.c_int, C.c_int]
     return lib
 
 
-def _softplus(v):
-    return np.where(v > 20.0, v, np.log1p(np.exp(np.minimum(v, 20.0))))
-
-
-def _silu(v):
-    return v / (1.0 + np.exp(-v))
-
-
-def boundary_ref(xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, seq, pset, rev, L):
-    """float64 restatement at the kernel boundary.  xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc)."""
-    njobs, E = delta.shape[0], delta.shape[1]
-    N = bc.shape[1] // 2
-    out = np.zeros((njobs, E, L))
-    for j in range(njobs):
-        s, p = seq[j], pset[j]
-        idx = np.arange(L)[::-1] if rev[j] else np.arange(L)      # logical time -> physical token
-        x = xz[s, :E, :L].astype(np.float64)[:, idx]
-        z = xz[s, E:, :L].astype(np.float64)[:, idx]
-        dr = delta[j, :, :L].astype(np.float64)[:, idx]
-        B = bc[j, :N, :L].astype(np.float64)[:, idx]
-        Cm = bc[j, N:, :L].astype(np.float64)[:, idx]
-        xp = np.concatenate([np.zeros((E, 3)), x], axis=1)
-        w = conv_w4[p].astype(np.float64)
-        u = _silu(conv_b[p].astype(np.float64)[:, None] + sum(w[:, k:k + 1] * xp[:, k:k + L] for k in range(4)))
-        dt = _softplus(dr + dt_b[p].astype(np.float64)[:, None])
-        a2 = A2[p].astype(np.float64)                              # (E, N), already * log2(e)
-        h = np.zeros((E, N))
-        y = np.zeros((E, L))
-        for t in range(L):
-            h = np.exp2(dt[:, t:t + 1] * a2) * h + (dt[:, t] * u[:, t])[:, None] * B[None, :, t]
-            y[:, t] = (h * Cm[None, :, t]).sum(1) + Dk[p].astype(np.float64) * u[:, t]
-        o = y * _silu(z)
-        out[j][:, idx] = o
-    return out
-
-
-def _problem(L, E, njobs_spec, dtype, seed):
-    """njobs_spec: list of (seq, pset, rev)."""
-    g = torch.Generator().manual_seed(seed)
-    N = 16
-    nseq = max(s for s, _, _ in njobs_spec) + 1
-    npset = max(p for _, p, _ in njobs_spec) + 1
-    njobs = len(njobs_spec)
-    ld = (L + 15) // 16 * 16
-    ldbc = (L + 31) // 32 * 32
-    xz = torch.randn(nseq, 2 * E, ld, generator=g).to(dtype)
-    xz[..., L:] = 7.0                                           # junk in the pad columns must not leak into [0, L)
-    delta = (torch.randn(njobs, E, ld, generator=g) * 1.5).to(dtype)
-    delta[..., L:] = 9.0
-    bc = torch.zeros(njobs, 2 * N, ldbc)
-    bc[..., :L] = torch.randn(njobs, 2 * N, L, generator=g)
-    conv_w4 = (0.5 * torch.randn(npset, E, 4, generator=g)).contiguous()
-    conv_b = 0.1 * torch.randn(npset, E, generator=g)
-    dt_b = torch.log(torch.expm1(torch.exp(torch.rand(npset, E, generator=g) * 4.6 - 6.9)))   # dt in [1e-3, 0.1]
-    dt_b[:, 0] = 25.0                                           # exercises the softplus threshold branch
-    A2 = (-torch.arange(1, N + 1, dtype=torch.float32).repeat(npset, E, 1)
-          * (0.5 + torch.rand(npset, E, 1, generator=g)) * 1.4426950408889634).contiguous()
-    Dk = torch.randn(npset, E, generator=g)
-    tabs = [torch.tensor([j[k] for j in njobs_spec], dtype=torch.int32) for k in range(3)]
-    return xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc
+from scan_boundary_ref import _problem, boundary_ref  # noqa: E402,F401  (re-exported for test_gpu_scan_v4.py)
 
 
 def _run_emu(lib, L, E, spec, dtype, G, seed):
@@ -107,7 +51,7 @@ def _run_emu(lib, L, E, spec, dtype, G, seed):
     a = _lib.ScanFwdArgs(p(xz), p(delta), p(bc), p(out), p(conv_w4), p(conv_b), p(dt_b), p(A2), p(Dk),
                          p(tabs[0]), p(tabs[1]), p(tabs[2]), None, None, None, None, None,
                          L, E, 16, 4, ld, ld, ldbc, ld, xz.shape[0], njobs, conv_w4.shape[0],
-                         _lib.CAD_BF16 if dtype == torch.bfloat16 else _lib.CAD_F16, G, 0, 0, 4)
+                         _lib.CAD_BF16 if dtype == torch.bfloat16 else _lib.CAD_F16, G, 0, 0, 4, None, 0)
     assert lib.emu_scan_v4(C.byref(a), G) == 0
     f = lambda t: t.float().numpy()   # noqa: E731
     ref = boundary_ref(f(xz), f(delta), f(bc), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk),

@@ -1,13 +1,16 @@
-"""GPU parity of the paired-channel scan kernel (cad_scan_fwd_args.variant = 4, csrc/scan_fwd_v4.cuh), through the C-ABI:
-against the float64 restatement at the kernel boundary (tests/test_emu_scan_v4.py::boundary_ref — the same checker the
-CPU emulation of this kernel is held to), against the one-channel-per-warp kernel (variant 3) on identical inputs,
-and end to end through the model against the fixture produced by the reference's own code."""
+"""GPU parity of the non-default forward-scan kernels (cad_scan_fwd_args.variant = 4 paired channels, 7 no replay,
+9 / 10 16-bit tile + barrier-free hand-over), through the C-ABI: against the float64 restatement at the kernel boundary
+(tests/scan_boundary_ref.py — the same checker the CPU emulation of these kernels is held to), against the default
+kernel (variant 3) on identical inputs, and end to end through the model against the fixture produced by the
+reference's own code."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from conftest import golden, tol
-from test_emu_scan_v4 import _problem, boundary_ref
+from scan_boundary_ref import _problem, boundary_ref
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -16,6 +19,7 @@ DEV = "cuda"
 def _run(L, E, spec, dtype, G, seed, variant):
     from caduceus_b200 import functional as CF
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, seed)
+    bc = bc.to(dtype).float()      # values every variant (fp32 or 16-bit tile) represents exactly
     d = lambda t: t.to(DEV).contiguous()   # noqa: E731
     out, _, _, _ = CF.scan_fwd(d(xz), d(delta), d(bc), tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)),
                                tuple(d(t) for t in tabs), L, channels_per_cta=G, variant=variant)
@@ -88,6 +92,48 @@ def test_v7_state_outputs_match_v3_fp32():
         if what == "out":
             got, ref = got[..., :L], ref[..., :L]
         assert torch.allclose(got, ref, rtol=2e-4, atol=2e-4 * float(ref.abs().max())), (what, (got - ref).abs().max())
+
+
+# Variants 9 / 10 have passed the CPU emulation of their source (tests/test_emu_scan_v9.py) but the round's GPU budget was
+# spent before their first hardware run: they are opt-in here until that run has happened.
+unmeasured = pytest.mark.skipif(os.environ.get("CAD_RUN_UNMEASURED") != "1",
+                                reason="variants 9 / 10: emulation-verified only; set CAD_RUN_UNMEASURED=1 to run on hardware")
+
+
+@unmeasured
+@pytest.mark.parametrize("variant", [9, 10])
+@pytest.mark.parametrize("L", [1, 17, 513, 2300])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_v9_v10_vs_boundary_restatement(L, rev, variant):
+    got, ref = _run(L, 64, [(0, 0, rev)], torch.bfloat16, 0, 300 + L, variant)
+    _check(got, ref, torch.bfloat16, f"v{variant} L={L} rev={rev}")
+
+
+@unmeasured
+@pytest.mark.parametrize("variant", [9, 10])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_v9_v10_hooks_vs_boundary_restatement(rev, variant):
+    """conv halo + carry-in; end state, sum dt and saved chunk states; then the state-only pass."""
+    from caduceus_b200 import functional as CF
+    L, E, dtype = 1700, 40, torch.float16
+    spec = [(0, 0, rev)]
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, 9)
+    bc = bc.to(dtype).float()
+    g = torch.Generator().manual_seed(1)
+    halo, h0 = torch.randn(1, E, 3, generator=g).to(dtype), torch.randn(1, E, 16, generator=g)
+    d = lambda t: t.to(DEV).contiguous()   # noqa: E731
+    args = (d(xz), d(delta), d(bc), tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)), tuple(d(t) for t in tabs), L)
+    out, hlast, dtsum, cstate = CF.scan_fwd(*args, halo=d(halo), h0=d(h0), want_state=True, want_chunk_state=True,
+                                            variant=variant)
+    _, hl2, ds2, _ = CF.scan_fwd(*args, halo=d(halo), h0=d(h0), state_only=True, variant=variant)
+    f = lambda t: t.float().numpy()   # noqa: E731
+    ref = boundary_ref(f(xz), f(delta), f(bc), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk), [0], [0], [rev], L,
+                       halo=f(halo), h0=f(h0), full=True)
+    _check(out[..., :L].float().cpu().numpy(), ref[0], dtype, "out")
+    for name, got, r in (("hlast", hlast, ref[1]), ("dtsum", dtsum, ref[2]), ("chunk_state", cstate, ref[3]),
+                         ("hlast (state-only)", hl2, ref[1]), ("dtsum (state-only)", ds2, ref[2])):
+        got = got.float().cpu().numpy()
+        assert np.allclose(got, r, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(r).max())), (name, np.abs(got - r).max())
 
 
 def test_v4_rejects_what_it_does_not_cover():
