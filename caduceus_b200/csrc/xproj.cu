@@ -5,6 +5,7 @@
 // touches HBM, x is read once, and the kernel writes exactly what the fused scan consumes:
 //     delta (njobs, E, ldd)   = W_dt . x_dbl[0:R]            io dtype (same rounding point as the reference pipeline)
 //     bc    (njobs, 2N, ldbc) = x_dbl[R:R+2N]                fp32, zero beyond the sequence end (TMA tile source)
+//     bc16  (njobs, 2N, ldbc16)  optionally, the same rows in the io dtype (tile source of scan variants 9 / 10)
 // Tensor cores are used for the two dense projections only (north_star): mma.sync m16n8k16 with fp32 accumulation;
 // both GEMMs are skinny (M = R+2N = 48 resp. K = R = 16) and the kernel is HBM-bound on the delta write, so
 // the legacy warp-level MMA path is already far above what the memory system needs (profiles/).
@@ -237,6 +238,11 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
             if (t + 1 < a.ldbc) *reinterpret_cast<float2*>(dst) = make_float2(t < L ? v0 : 0.f, t + 1 < L ? v1 : 0.f);
             else dst[0] = t < L ? v0 : 0.f;
           }
+          if (a.bc16 && t < a.ldbc16) {        // the same rows in the io dtype: tile source of scan variants 9 / 10
+            T* d16 = static_cast<T*>(a.bc16) + ((int64_t)job * 2 * N + (r - R)) * a.ldbc16 + t;
+            if (t + 1 < a.ldbc16) *reinterpret_cast<uint32_t*>(d16) = pack2<T>(t < L ? v0 : 0.f, t + 1 < L ? v1 : 0.f);
+            else d16[0] = io<T>::from_f(t < L ? v0 : 0.f);
+          }
         }
       }
   __syncthreads();
@@ -291,6 +297,8 @@ extern "C" int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream_) {
               "cad_conv_xproj_fwd: bad row pitches");
   CAD_REQUIRE(aligned16(a->xz) && aligned16(a->delta) && aligned16(a->w_x) && ((uintptr_t)a->bc & 7) == 0 &&
               a->ldbc % 2 == 0, "cad_conv_xproj_fwd: alignment");
+  CAD_REQUIRE(!a->bc16 || (((uintptr_t)a->bc16 & 3) == 0 && a->ldbc16 % 2 == 0 && a->ldbc16 >= a->L),
+              "cad_conv_xproj_fwd: bc16 must be 4-byte aligned with an even pitch >= L");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   static_assert(2 * KC * XP >= 8 * 16 * UP, "output staging must fit in the x slabs it aliases");
   const size_t smem = sizeof(uint16_t) * ((size_t)2 * KC * XP + 2 * MROWS * WP + KC * UP + (size_t)a->E * DP + 16 * UP) +

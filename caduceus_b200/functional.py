@@ -253,9 +253,10 @@ def conv_xproj_supported(xz, N, R):
     return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 1024
 
 
-def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None):
+def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=False):
     """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores: returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32)
-    without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype."""
+    without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.  want_bc16: also return the
+    B / C rows in the activation dtype (njobs, 2N, ceil64(L)) — the tile source of scan variants 9 / 10."""
     lib = _lib.load()
     seq, pset, rev = jobs
     nseq, twoE, ld = xz.shape
@@ -266,12 +267,13 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None):
     ldbc = round_up(max(L, 1), 32)
     delta = torch.empty(njobs, E, ld, device=xz.device, dtype=xz.dtype)
     bc = torch.empty(njobs, 2 * N, ldbc, device=xz.device, dtype=torch.float32)
+    bc16 = torch.empty(njobs, 2 * N, round_up(max(L, 1), 64), device=xz.device, dtype=xz.dtype) if want_bc16 else None
     a = _lib.ConvXprojArgs(_ptr(xz), _ptr(w_x.contiguous()), _ptr(w_dt.contiguous()), _ptr(conv_w4), _ptr(conv_b),
                            _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(delta), _ptr(bc),
-                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz))
+                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), _ptr(bc16), bc16.stride(1) if want_bc16 else 0)
     _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
     _launched()
-    return delta, bc
+    return (delta, bc, bc16) if want_bc16 else (delta, bc)
 
 
 def project_dt_bc(xdbl, dt_w_job, L, N):

@@ -257,8 +257,14 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
         halo = seqshard.gather_halo(xz[:, :E, :], L, jobs[0], jobs[2], shard).to(act)
     if CF.conv_xproj_supported(xz, N, m0.dt_rank) and not _FORCE_UNFUSED_XPROJ:
         # one tensor-core kernel: conv+SiLU -> x_proj -> dt_proj; u never touches HBM
-        delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo)
+        bc16 = None
+        if CF.SCAN_VARIANT in (9, 10):     # 16-bit-tile scan variants: the tile source comes straight from this kernel
+            delta, bc, bc16 = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo,
+                                            want_bc16=True)
+        else:
+            delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo)
     else:
+        bc16 = None
         u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                    # (njobs, E, Lp)
         wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
         xdbl = torch.bmm(wx_job, u)                                                       # (njobs, R+2N, Lp)
@@ -269,11 +275,11 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
 
     # ---- fused scan --------------------------------------------------------------------------------------
     if not sharded:
-        yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L)
+        yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, bc16=bc16)
     else:
         # zero-carry scan (outputs + end state + sum dt) -> ONE all_gather -> compose this shard's carry-in ->
         # add its decaying contribution in place (seqshard.py, csrc/scan_fixup.cu).  Ranks never wait for each other.
-        yg, hl, ds, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True)
+        yg, hl, ds, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True, bc16=bc16)
         h0 = seqshard.gather_carry(hl, ds, packed[3], jobs[1], jobs[2], shard)
         CF.scan_fixup(xz, delta, bc, yg, packed, jobs, L, h0)
     del xz

@@ -230,7 +230,8 @@ int cad_conv_silu_bwd(const cad_conv_bwd_args* a, void* stream);
  *      cad_bimamba_scan_fwd without materialising u = silu(conv(x)).  Replaces causal_conv1d_fwd + the x_proj and
  *      dt_proj GEMMs of upstream's mamba_inner_fn.
  *        w_x (P, R+2N, E), w_dt (P, E, R) in the io dtype;  delta (njobs, E, ldd) io dtype;
- *        bc (njobs, 2N, ldbc) fp32, written for every column < ldbc (zeros beyond L).
+ *        bc (njobs, 2N, ldbc) fp32, written for every column < ldbc (zeros beyond L);
+ *        bc16 (njobs, 2N, ldbc16) optional (NULL): the same rows in the io dtype, ldbc16 even, for scan variants 9 / 10.
  *      Constraints: io dtype f16/bf16, N == 16, R <= 16, E % 64 == 0; otherwise use cad_conv_silu_fwd + GEMMs.   */
 typedef struct {
   const void* xz; const void* w_x; const void* w_dt;
@@ -241,6 +242,7 @@ typedef struct {
   int64_t L, E, N, R;
   int64_t ldxz, ldd, ldbc;
   int32_t nseq, njobs, io_dtype;
+  void* bc16; int64_t ldbc16;
 } cad_conv_xproj_args;
 int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
 

@@ -145,9 +145,11 @@ def test_v4_rejects_what_it_does_not_cover():
                     tuple(d(t) for t in tabs), 100, variant=4)
 
 
+@pytest.mark.parametrize("variant", [4, pytest.param(9, marks=unmeasured), pytest.param(10, marks=unmeasured)])
 @pytest.mark.parametrize("tag", ["ps_small", "ph_config0"])
-def test_model_forward_with_v4_vs_reference_fixture(tag):
-    """The whole model with the scan forced to variant 4, against the logits the reference's own code produced."""
+def test_model_forward_with_scan_variant_vs_reference_fixture(tag, variant):
+    """The whole model with the scan forced to a non-default variant (9 / 10 take their 16-bit tile straight from the
+    conv_xproj kernel), against the logits the reference's own code produced."""
     import caduceus
     from caduceus_b200 import functional as CF
     fx = golden(f"model_{tag}.pt")
@@ -158,14 +160,14 @@ def test_model_forward_with_v4_vs_reference_fixture(tag):
     launches = []
     orig = CF.scan_variant
     try:
-        CF.SCAN_VARIANT = 4
+        CF.SCAN_VARIANT = variant
         CF.scan_variant = lambda a: launches.append(orig(a)) or launches[-1]
         with torch.no_grad():
             logits = model(fx["input_ids"].to(DEV)).logits.float().cpu()
     finally:
         CF.SCAN_VARIANT = 0
         CF.scan_variant = orig
-    assert launches and all(v == 4 for v in launches), launches
+    assert launches and all(v == variant for v in launches), launches
     # same criterion as test_gpu_parity.py::test_model_low_precision_vs_reference_fixture (16-bit stack vs fp32 fixture)
     rtol, atol = tol(torch.bfloat16)
     scale = fx["logits"].abs().max().item()
