@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--graph", action="store_true",
                     help="replay the forward from a CUDA graph (single-GPU / replica forward only; helps short sequences)")
     ap.add_argument("--scan-tok", type=int, default=0, choices=[0, 8, 16], help="tokens per lane of the scan kernel (tuning)")
-    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4, 7, 9, 10],
+    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4, 7, 9, 10, 11, 12],
                     help="forward-scan kernel variant (cad_scan_fwd_args.variant); default: env CAD_SCAN_VARIANT / library default")
     ap.add_argument("--shard", default="none", choices=["none", "seq"],
                     help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")

@@ -462,23 +462,40 @@ static bool v4_supported(const cad_scan_fwd_args& a) {
          !a.chunk_state && !a.state_only && (a.tokens_per_lane == 0 || a.tokens_per_lane == 16);
 }
 
-// ---- v9 / v10: 16-bit B/C tile, barrier-free tile hand-over, no replay, optional exp2 pipeline (scan_fwd_v9.cuh) ----
+// ---- v9 .. v12: barrier-free tile hand-over, no replay, optional exp2 pipeline (scan_fwd_v9.cuh) ----------------------
+//      9 / 10: 16-bit tile, <= 7 warps, two CTAs per SM;   11 / 12: fp32 tile shared by <= 14 warps, one CTA per SM
 template <typename T, bool STATE_ONLY, bool PIPE>
-__global__ void __launch_bounds__(v9::kMaxG9 * 32, 2)
+__global__ void __launch_bounds__(7 * 32, 2)
 bimamba_scan_fwd_v9_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_raw[];
-  v9::kernel_body<T, STATE_ONLY, PIPE>(a, &tmap, smem_raw);
+  v9::kernel_body<T, T, STATE_ONLY, PIPE>(a, &tmap, smem_raw);
+}
+// 14 warps must fit the register file of ONE SM partition-wise: 4 warps x 32 x 128 = 16 K registers per scheduler
+template <typename T, bool STATE_ONLY, bool PIPE>
+__global__ void __maxnreg__(128)
+bimamba_scan_fwd_v11_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ unsigned char smem_raw[];
+  v9::kernel_body<T, float, STATE_ONLY, PIPE>(a, &tmap, smem_raw);
 }
 
 template <typename T>
-static int launch_scan_v9(const cad_scan_fwd_args& a, int G, bool pipe, cudaStream_t stream) {
+static int launch_scan_v9(const cad_scan_fwd_args& a, int G, bool pipe, bool tile32, cudaStream_t stream) {
   CUtensorMap tmap;
-  if (make_row_tile_map16(&tmap, a.bc16, a.io_dtype == CAD_BF16, (int64_t)a.njobs * 2 * v9::NST, a.ldbc16, a.L, 2 * v9::NST,
-                          v9::CH) != 0) return -1;
-  const size_t smem = v9::smem_bytes(G, sizeof(T));
+  if (tile32) {
+    if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * v9::NST, a.ldbc, a.L, 2 * v9::NST, v9::CH) != 0) return -1;
+  } else {
+    if (make_row_tile_map16(&tmap, a.bc16, a.io_dtype == CAD_BF16, (int64_t)a.njobs * 2 * v9::NST, a.ldbc16, a.L,
+                            2 * v9::NST, v9::CH) != 0) return -1;
+  }
+  const size_t smem = v9::smem_bytes(G, sizeof(T), tile32 ? 4 : sizeof(T));
   void (*kern)(const cad_scan_fwd_args, const CUtensorMap);
-  if (a.state_only) kern = pipe ? bimamba_scan_fwd_v9_kernel<T, true, true> : bimamba_scan_fwd_v9_kernel<T, true, false>;
-  else              kern = pipe ? bimamba_scan_fwd_v9_kernel<T, false, true> : bimamba_scan_fwd_v9_kernel<T, false, false>;
+  if (tile32) {
+    if (a.state_only) kern = pipe ? bimamba_scan_fwd_v11_kernel<T, true, true> : bimamba_scan_fwd_v11_kernel<T, true, false>;
+    else              kern = pipe ? bimamba_scan_fwd_v11_kernel<T, false, true> : bimamba_scan_fwd_v11_kernel<T, false, false>;
+  } else {
+    if (a.state_only) kern = pipe ? bimamba_scan_fwd_v9_kernel<T, true, true> : bimamba_scan_fwd_v9_kernel<T, true, false>;
+    else              kern = pipe ? bimamba_scan_fwd_v9_kernel<T, false, true> : bimamba_scan_fwd_v9_kernel<T, false, false>;
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(v9): %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
@@ -496,7 +513,7 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   CAD_REQUIRE(a, "cad_bimamba_scan_fwd: null argument block");
   CAD_REQUIRE(a->L >= 0 && a->E > 0 && a->njobs > 0 && a->nseq > 0, "cad_bimamba_scan_fwd: bad sizes");
   if (a->L == 0) return 0;
-  CAD_REQUIRE(a->xz && a->delta && (a->bc || a->variant >= 9) && (a->out || a->state_only) && a->conv_w && a->conv_b && a->dt_b && a->A2 && a->Dskip &&
+  CAD_REQUIRE(a->xz && a->delta && (a->bc || a->variant == 9 || a->variant == 10) && (a->out || a->state_only) && a->conv_w && a->conv_b && a->dt_b && a->A2 && a->Dskip &&
               a->seq_of_job && a->pset_of_job && a->rev_of_job, "cad_bimamba_scan_fwd: null pointer");
   CAD_REQUIRE(a->N == 16, "cad_bimamba_scan_fwd: d_state = %lld not built (only 16)", (long long)a->N);
   CAD_REQUIRE(a->K >= 1 && a->K <= 4, "cad_bimamba_scan_fwd: d_conv = %lld out of range [1, 4]", (long long)a->K);
@@ -507,8 +524,8 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
               "cad_bimamba_scan_fwd: xz/delta/bc/out must be 16-byte aligned");
   CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4 || a->variant == 7 || a->variant == 9 || a->variant == 10,
-              "cad_bimamba_scan_fwd: variant must be 0, 3, 4, 7, 9 or 10");
+  CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4 || a->variant == 7 || (a->variant >= 9 && a->variant <= 12),
+              "cad_bimamba_scan_fwd: variant must be 0, 3, 4, 7 or 9..12");
   if (a->variant == 4) {
     CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
                 "halo / h0 / hlast / dtsum / chunk_state / state_only");
@@ -538,12 +555,26 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
     }
   }
   CAD_REQUIRE(G >= 1 && G <= kMaxG, "cad_bimamba_scan_fwd: channels_per_cta must be in [1, %d]", kMaxG);
-  if (a->variant == 9 || a->variant == 10) {
-    CAD_REQUIRE(a->io_dtype != CAD_F32, "cad_bimamba_scan_fwd: variants 9 / 10 need 16-bit I/O");
-    CAD_REQUIRE(a->bc16 && aligned16(a->bc16) && a->ldbc16 % 64 == 0 && a->ldbc16 >= a->L,
+  if (a->variant >= 9) {
+    const bool tile32 = a->variant >= 11, pipe = (a->variant == 10 || a->variant == 12);
+    CAD_REQUIRE(a->io_dtype != CAD_F32, "cad_bimamba_scan_fwd: variants 9..12 need 16-bit I/O");
+    CAD_REQUIRE(tile32 || (a->bc16 && aligned16(a->bc16) && a->ldbc16 % 64 == 0 && a->ldbc16 >= a->L),
                 "cad_bimamba_scan_fwd: variants 9 / 10 need bc16 (16-byte aligned, ldbc16 a multiple of 64 and >= L)");
-    if (a->io_dtype == CAD_BF16) return launch_scan_v9<__nv_bfloat16>(*a, G, a->variant == 10, stream);
-    return launch_scan_v9<__half>(*a, G, a->variant == 10, stream);
+    int G9 = a->channels_per_cta;
+    const int gmax = tile32 ? v9::kMaxG9 : 7;
+    if (G9 <= 0) {
+      const int sms = cad_sm_count() > 0 ? cad_sm_count() : 148;
+      const int per_sm = tile32 ? 1 : 2;       // resident CTAs per SM
+      long best = -1;
+      for (int g = 1; g <= gmax; ++g) {
+        const long ctas = (long)a->njobs * ((a->E + g - 1) / g);
+        const long cost = ((ctas + (long)sms * per_sm - 1) / ((long)sms * per_sm)) * g;
+        if (best < 0 || cost <= best) { best = cost; G9 = g; }
+      }
+    }
+    CAD_REQUIRE(G9 >= 1 && G9 <= gmax, "cad_bimamba_scan_fwd: channels_per_cta must be in [1, %d] for this variant", gmax);
+    if (a->io_dtype == CAD_BF16) return launch_scan_v9<__nv_bfloat16>(*a, G9, pipe, tile32, stream);
+    return launch_scan_v9<__half>(*a, G9, pipe, tile32, stream);
   }
   // tokens per lane: 16 (512-token chunks, 2 CTAs/SM) or 8 (256-token chunks, up to 4 CTAs/SM, 16-bit I/O only).
   // The saved chunk states (training) are defined on 512-token chunks, so they force 16.

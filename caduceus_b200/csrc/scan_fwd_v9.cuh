@@ -15,6 +15,10 @@
 //   * an EXP2 SOFTWARE PIPELINE (template PIPE): the 16 exp2 of state n+1 are issued right before state n's shuffle
 //     rounds, so the MUFU pipe has work while the warp waits on SHFL round trips.
 //
+// Template TT chooses the tile element type: the io dtype (variants 9 / 10: 2 x 32 KB, up to 7 warps, two CTAs per SM) or
+// float (variants 11 / 12: 2 x 64 KB shared by up to 14 warps in ONE CTA per SM — no unpack instructions, half the TMA
+// tile traffic per channel, same barrier-free hand-over).
+//
 // Same operator, argument block and hooks as scan_fwd.cu (conv halo, carry-in h0, end state, sum dt, saved chunk states,
 // state-only pass) for 16-bit I/O; fp32 I/O stays on variant 3.  ref call chain: ref:caduceus/modeling_caduceus.py:128-137,
 // ref:caduceus/modeling_rcps.py:85-99 -> upstream selective_scan_fwd / causal_conv1d_fwd.
@@ -48,14 +52,21 @@ constexpr int TOK = 16;             // tokens per lane
 constexpr int NP = TOK / 2;         // physical token pairs per lane
 constexpr int CH = 32 * TOK;        // 512 tokens per chunk
 constexpr int NST = 16;             // d_state
-constexpr int kMaxG9 = 7;           // warps (channels) per CTA
-constexpr int kLineTok = 64;        // 16-bit tokens per 128-byte swizzle line
-constexpr int kRowBytes = CH * 2;   // one tile row: 512 tokens x 2 bytes = 8 lines
-constexpr int kTileBytes = 2 * NST * kRowBytes;     // 32 KB
+constexpr int kMaxG9 = 14;          // warps (channels) per CTA: <= 7 with a 16-bit tile (two CTAs per SM), <= 14 with an
+                                    // fp32 tile (one CTA per SM; its two 64 KB buffers are shared by 14 channels)
 constexpr int kRows = 3;            // staged rows per warp: x, dt_raw, z
+// tile geometry for a tile element type TT (the io dtype, or float): a 128-byte swizzle line holds 128 / sizeof(TT)
+// tokens; a tile row is 512 tokens; the tile is 2 N rows
+template <typename TT> struct tile_geom {
+  static constexpr int kLineTok = 128 / (int)sizeof(TT);
+  static constexpr int kRowBytes = CH * (int)sizeof(TT);
+  static constexpr int kTileBytes = 2 * NST * kRowBytes;          // 32 KB (16-bit) or 64 KB (fp32)
+  static constexpr int kPieces = TOK * (int)sizeof(TT) / 16;      // 16-byte pieces per lane segment: 2 or 4
+  static constexpr int kPairsPerPiece = NP / kPieces;             // 4 or 2
+};
 
 struct Smem {
-  uint32_t tile[2];    // shared-space byte addresses of the two 16-bit B/C tiles (1024-byte aligned)
+  uint32_t tile[2];    // shared-space byte addresses of the two B/C tiles (1024-byte aligned)
   uint32_t par;        // [G][8] floats: conv taps 0..3, conv bias, dt bias, D, pad
   uint32_t a2;         // [G][NST]
   uint32_t carry;      // [G][NST] running state of each warp's channel
@@ -73,23 +84,32 @@ template <> CAD_DEV float2 unpack2<__half>(uint32_t w) {
   return make_float2(__half2float(__low2half(h)), __half2float(__high2half(h)));
 }
 
-// this lane's two 16-byte pieces (8 tokens each) inside a swizzled 16-bit tile row: SWIZZLE_128B stores 16-byte chunk c
-// of 128-byte line l at position c ^ (l & 7); a row is 8 lines of 64 tokens, so l & 7 == line-in-row.
-CAD_DEV void piece_offsets16(int seg, uint32_t (&poff)[2]) {
-  const int line = seg >> 2, c0 = 2 * (seg & 3);
+// this lane's 16-byte pieces inside a swizzled tile row: SWIZZLE_128B stores 16-byte chunk c of 128-byte line l at
+// position c ^ (l & 7); a row is 8 (16-bit) or 16 (fp32) lines, so l & 7 == (line-in-row) & 7.
+template <typename TT>
+CAD_DEV void piece_offsets(int seg, uint32_t (&poff)[4]) {
+  constexpr int P = tile_geom<TT>::kPieces, SPL = 8 / P;          // lane segments per line: 4 or 2
+  const int line = seg / SPL, c0 = P * (seg % SPL);
 #pragma unroll
-  for (int k = 0; k < 2; ++k) poff[k] = line * 128 + (((c0 + k) ^ line) << 4);
+  for (int k = 0; k < 4; ++k) poff[k] = k < P ? line * 128 + (((c0 + k) ^ (line & 7)) << 4) : 0u;
+}
+// the k-th physical token pair of a 16-byte piece -> fp32 pair
+template <typename T, typename TT>
+CAD_DEV float2 piece_pair(const uint4& q, int m) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  if constexpr (sizeof(TT) == 2) return unpack2<T>(w[m]);
+  else return make_float2(u2f(w[2 * m]), u2f(w[2 * m + 1]));
 }
 
 struct ChunkCtx {
   int lane, sg, G;
-  uint32_t poff[2];
+  uint32_t poff[4];
   uint32_t par_s, a2_s, carry_s;
   uint32_t pre_cur, pre_next;
   bool active;
 };
 
-template <typename T, bool REV, bool TAIL, bool STATE_ONLY, bool PIPE>
+template <typename T, typename TT, bool REV, bool TAIL, bool STATE_ONLY, bool PIPE>
 CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& cx, const tmap_t* tmap, float (&prev3)[3],
                    const float (&hal)[3], float& dt_total, int64_t tseg, int64_t tseg_next, bool stage_next,
                    const T* __restrict__ g_x, const T* __restrict__ g_d, T* __restrict__ g_o, int buf, uint32_t parity,
@@ -101,6 +121,7 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
   auto halo_at = [&](int64_t tau) { return tau == -1 ? hal[2] : (tau == -2 ? hal[1] : (tau == -3 ? hal[0] : 0.f)); };
   const bool seg_in = !TAIL || tseg < L;
   constexpr uint32_t ROW = CH * sizeof(T);
+  using TG = tile_geom<TT>;
 
   float2 dt2[NP], du2[NP], y2[NP];
   float dsum = 0.f;
@@ -178,17 +199,16 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
     float hl = 0.f, pc = 1.f;
     float2 g2[NP];
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {                       // 16-byte pieces (8 tokens) in logical order
-      const int k = REV ? 1 - kk : kk;
-      const uint4 bq = lds128u(tile_s + n * kRowBytes + cx.poff[k]);
+    for (int kk = 0; kk < TG::kPieces; ++kk) {             // 16-byte pieces of the tile rows in logical order
+      const int k = REV ? TG::kPieces - 1 - kk : kk;
+      const uint4 bq = lds128u(tile_s + n * TG::kRowBytes + cx.poff[k]);
       uint4 cq = make_uint4(0u, 0u, 0u, 0u);
-      if (!STATE_ONLY) cq = lds128u(tile_s + (NST + n) * kRowBytes + cx.poff[k]);
-      const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w}, cwd[4] = {cq.x, cq.y, cq.z, cq.w};
+      if (!STATE_ONLY) cq = lds128u(tile_s + (NST + n) * TG::kRowBytes + cx.poff[k]);
 #pragma unroll
-      for (int mm = 0; mm < 4; ++mm) {
-        const int m = REV ? 3 - mm : mm;
-        const int j = 4 * k + m;                           // physical pair (tokens 2j, 2j+1) of the segment
-        const float2 bv = mul2(du2[j], unpack2<T>(bw[m]));
+      for (int mm = 0; mm < TG::kPairsPerPiece; ++mm) {
+        const int m = REV ? TG::kPairsPerPiece - 1 - mm : mm;
+        const int j = TG::kPairsPerPiece * k + m;          // physical pair (tokens 2j, 2j+1) of the segment
+        const float2 bv = mul2(du2[j], piece_pair<T, TT>(bq, m));
         float2 hp, pp;
         if (REV) {
           hl = fmaf(av[j].y, hl, bv.y); hp.y = hl; pc *= av[j].y; pp.y = pc;
@@ -198,7 +218,7 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
           hl = fmaf(av[j].y, hl, bv.y); hp.y = hl; pc *= av[j].y; pp.y = pc;
         }
         if (!STATE_ONLY) {
-          const float2 cp = unpack2<T>(cwd[m]);
+          const float2 cp = piece_pair<T, TT>(cq, m);
           y2[j] = fma2(cp, hp, y2[j]);
           g2[j] = mul2(cp, pp);
         }
@@ -247,8 +267,8 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
     if (atomic_inc_shared(cnt_s) == (uint32_t)(cx.G - 1)) {
       sts32u(cnt_s, 0u);
       if (issue_tma) {
-        mbar_expect_tx(&sm.bar[buf], kTileBytes);
-        tma_load_3d(sm.base + (buf ? kTileBytes : 0), tmap, 0, tma_c1, job_row, &sm.bar[buf]);
+        mbar_expect_tx(&sm.bar[buf], TG::kTileBytes);
+        tma_load_3d(sm.base + (buf ? TG::kTileBytes : 0), tmap, 0, tma_c1, job_row, &sm.bar[buf]);
       }
     }
   }
@@ -280,7 +300,7 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
   }
 }
 
-template <typename T, bool REV, bool STATE_ONLY, bool PIPE>
+template <typename T, typename TT, bool REV, bool STATE_ONLY, bool PIPE>
 CAD_DEV void run_job(const cad_scan_fwd_args& a, const tmap_t* tmap, int job, int seq, int pset, const Smem& sm) {
   const int lane = CAD_TID & 31, warp = CAD_TID >> 5, G = CAD_NTHREADS >> 5;
   const int64_t L = a.L, E = a.E;
@@ -325,16 +345,17 @@ CAD_DEV void run_job(const cad_scan_fwd_args& a, const tmap_t* tmap, int job, in
   float dt_total = 0.f;
 
   cx.sg = REV ? 31 - lane : lane;
-  piece_offsets16(cx.sg, cx.poff);
+  using TG = tile_geom<TT>;
+  piece_offsets<TT>(cx.sg, cx.poff);
   const int job_row = job * 2 * NST;
-  constexpr int BPC = CH / kLineTok;            // 8 swizzle lines per chunk row
+  constexpr int BPC = CH / TG::kLineTok;        // swizzle lines per chunk row: 8 (16-bit) or 16 (fp32)
 
   cta_sync();                                   // barrier init + parameter staging visible
   if (CAD_TID == 0) {
     for (int k = 0; k < 2 && k < nchunks; ++k) {
       const int64_t pci = REV ? nchunks - 1 - k : k;
-      mbar_expect_tx(&sm.bar[k], kTileBytes);
-      tma_load_3d(sm.base + (k ? kTileBytes : 0), tmap, 0, (int)(pci * BPC), job_row, &sm.bar[k]);
+      mbar_expect_tx(&sm.bar[k], TG::kTileBytes);
+      tma_load_3d(sm.base + (k ? TG::kTileBytes : 0), tmap, 0, (int)(pci * BPC), job_row, &sm.bar[k]);
     }
   }
 
@@ -373,10 +394,10 @@ CAD_DEV void run_job(const cad_scan_fwd_args& a, const tmap_t* tmap, int job, in
     cx.pre_cur = pre_addr(buf);
     cx.pre_next = pre_addr(buf ^ 1);
     if (tail)
-      chunk<T, REV, true, STATE_ONLY, PIPE>(a, sm, cx, tmap, prev3, hal, dt_total, tseg, tseg_next, stage_next, g_x, g_d, g_o,
+      chunk<T, TT, REV, true, STATE_ONLY, PIPE>(a, sm, cx, tmap, prev3, hal, dt_total, tseg, tseg_next, stage_next, g_x, g_d, g_o,
                                             buf, parity, issue_tma, tma_c1, job_row);
     else
-      chunk<T, REV, false, STATE_ONLY, PIPE>(a, sm, cx, tmap, prev3, hal, dt_total, tseg, tseg_next, stage_next, g_x, g_d, g_o,
+      chunk<T, TT, REV, false, STATE_ONLY, PIPE>(a, sm, cx, tmap, prev3, hal, dt_total, tseg, tseg_next, stage_next, g_x, g_d, g_o,
                                              buf, parity, issue_tma, tma_c1, job_row);
     if (a.chunk_state) {                        // state at the end of each 512-token logical chunk (saved for backward)
       warp_sync();
@@ -397,27 +418,30 @@ CAD_DEV void run_job(const cad_scan_fwd_args& a, const tmap_t* tmap, int job, in
 }
 
 // shared-memory plan (bytes from the 1024-aligned base): two tiles | par | a2 | carry | counters + bars | staging
+template <typename TT>
 CAD_DEV void carve(unsigned char* base, Smem& sm) {
+  constexpr int TB = tile_geom<TT>::kTileBytes;
   const uint32_t b = smem_u32(base);
   sm.base = base;
   sm.tile[0] = b;
-  sm.tile[1] = b + kTileBytes;
-  sm.par = b + 2 * kTileBytes;
+  sm.tile[1] = b + TB;
+  sm.par = b + 2 * TB;
   sm.a2 = sm.par + kMaxG9 * 32;
   sm.carry = sm.a2 + kMaxG9 * NST * 4;
   sm.cnt = sm.carry + kMaxG9 * NST * 4;
-  sm.bar = reinterpret_cast<uint64_t*>(base + 2 * kTileBytes + kMaxG9 * 32 + 2 * kMaxG9 * NST * 4 + 16);
+  sm.bar = reinterpret_cast<uint64_t*>(base + 2 * TB + kMaxG9 * 32 + 2 * kMaxG9 * NST * 4 + 16);
   sm.pre = sm.cnt + 16 + 16;
 }
-inline size_t smem_bytes(int G, size_t elem) {
-  return 1024 + (size_t)2 * kTileBytes + kMaxG9 * 32 + (size_t)2 * kMaxG9 * NST * 4 + 32 + (size_t)2 * G * kRows * CH * elem;
+inline size_t smem_bytes(int G, size_t elem, size_t tile_elem) {
+  return 1024 + (size_t)2 * (2 * NST * CH * tile_elem) + kMaxG9 * 32 + (size_t)2 * kMaxG9 * NST * 4 + 32 +
+         (size_t)2 * G * kRows * CH * elem;
 }
 
-template <typename T, bool STATE_ONLY, bool PIPE>
+template <typename T, typename TT, bool STATE_ONLY, bool PIPE>
 CAD_DEV void kernel_body(const cad_scan_fwd_args& a, const tmap_t* tmap, unsigned char* smem_raw) {
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Smem sm;
-  carve(base, sm);
+  carve<TT>(base, sm);
   if (CAD_TID == 0) {
     mbar_init(&sm.bar[0], 1);
     mbar_init(&sm.bar[1], 1);
@@ -426,8 +450,8 @@ CAD_DEV void kernel_body(const cad_scan_fwd_args& a, const tmap_t* tmap, unsigne
   }
   const int job = CAD_BIDY;
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
-  if (rev) run_job<T, true, STATE_ONLY, PIPE>(a, tmap, job, seq, pset, sm);
-  else     run_job<T, false, STATE_ONLY, PIPE>(a, tmap, job, seq, pset, sm);
+  if (rev) run_job<T, TT, true, STATE_ONLY, PIPE>(a, tmap, job, seq, pset, sm);
+  else     run_job<T, TT, false, STATE_ONLY, PIPE>(a, tmap, job, seq, pset, sm);
 }
 
 }  // namespace v9

@@ -15,7 +15,7 @@ _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
 SCAN_TOKENS_PER_LANE = 0   # 0 = library default; 8 / 16 force the scan's tokens per lane (tuning knob)
-SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7 / 9 / 10: see cad_scan_fwd_args.variant
+SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7 / 9..12: see cad_scan_fwd_args.variant
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
 
@@ -340,7 +340,7 @@ def scan_variant(a):
         ok = (a.io_dtype != CAD_F32 and a.N == 16 and a.E % 2 == 0 and not (a.halo or a.h0 or a.hlast or a.dtsum
               or a.chunk_state) and not a.state_only and a.tokens_per_lane in (0, 16))
         return 4 if ok else 0
-    if SCAN_VARIANT in (9, 10):
+    if SCAN_VARIANT in (9, 10, 11, 12):
         return SCAN_VARIANT if (a.io_dtype != CAD_F32 and a.N == 16 and a.tokens_per_lane in (0, 16)) else 0
     return SCAN_VARIANT
 

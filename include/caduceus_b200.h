@@ -149,10 +149,11 @@ typedef struct {
                                pass; 7 = 3 with token pairs packed (FMUL2 / FFMA2) and no replay pass (16 tokens per
                                lane); 9 / 10 = 7's state loop on a 16-BIT B/C tile (bc16), two tile buffers handed over
                                through mbarriers + arrival counters instead of a per-chunk CTA barrier, 10 adds the
-                               exp2 software pipeline (16-bit I/O; all hooks); 4 = two channels per warp with packed
+                               exp2 software pipeline (16-bit I/O; all hooks); 11 / 12 = the same with an fp32 tile
+                               (bc) shared by up to 14 channels in one CTA per SM; 4 = two channels per warp with packed
                                fp32 (inference only: 16-bit I/O, even E, no sharding hooks / saved states — an error
                                otherwise; channels_per_cta then counts channel PAIRS) */
-  const void* bc16;         /* variants 9 / 10: (njobs, 2N, ldbc16) B / C rows in the I/O dtype, zeros in [L, ldbc16) */
+  const void* bc16;         /* variants 9 / 10 only: (njobs, 2N, ldbc16) B / C rows in the I/O dtype, zeros in [L, ldbc16) */
   int64_t ldbc16;           /* multiple of 64 elements, >= L */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);

@@ -4,12 +4,12 @@
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/r2_first_call.log) 2>&1
 date; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-echo "== hardware parity of scan variants 9 / 10 (16-bit tile, barrier-free hand-over) and of conv_xproj's bc16 output"; date
+echo "== hardware parity of scan variants 9..12 (barrier-free hand-over; 16-bit / fp32 tile) and of conv_xproj's bc16 output"; date
 CAD_RUN_UNMEASURED=1 timeout 300 python -m pytest tests/test_gpu_scan_variants.py -m gpu -q --timeout 120 2>&1 | tail -8
 echo "== A/B timing on the headline shapes"; date
-timeout 200 python scripts/time_scan_variants.py --model ps,ph --variants 3,7,9,10,4 | tee gpurun_out/r2_ab_scan.jsonl
+timeout 200 python scripts/time_scan_variants.py --model ps,ph --variants 3,7,9,10,11,12,4 | tee gpurun_out/r2_ab_scan.jsonl
 echo "== bench with the scan forced to 10 / 9 / default"; date
-for v in 10 9 3; do
+for v in 10 12 3; do
   timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --scan-variant $v | tee gpurun_out/r2_bench_ps_scan_v$v.json
 done
 echo "== ncu --set full of variant 10"; date

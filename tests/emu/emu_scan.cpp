@@ -61,36 +61,44 @@ extern "C" int emu_scan_v4(const cad_scan_fwd_args* a, int G) {
   return 0;
 }
 
-template <typename T>
+template <typename T, typename TT>
 static void run_v9(const cad_scan_fwd_args* a, const cad::EmuTmap* tmap, int G, int bx, int by, int pipe) {
   using namespace cad;
-  const size_t sb = v9::smem_bytes(G, sizeof(T));
+  const size_t sb = v9::smem_bytes(G, sizeof(T), sizeof(TT));
   if (a->state_only) {
-    if (pipe) run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, true, true>(*a, tmap, sm); });
-    else      run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, true, false>(*a, tmap, sm); });
+    if (pipe) run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, TT, true, true>(*a, tmap, sm); });
+    else      run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, TT, true, false>(*a, tmap, sm); });
   } else {
-    if (pipe) run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, false, true>(*a, tmap, sm); });
-    else      run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, false, false>(*a, tmap, sm); });
+    if (pipe) run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, TT, false, true>(*a, tmap, sm); });
+    else      run_cta(sb, G, bx, by, [&](unsigned char* sm) { v9::kernel_body<T, TT, false, false>(*a, tmap, sm); });
   }
 }
 
-extern "C" int emu_scan_v9(const cad_scan_fwd_args* a, int G, int pipe) {
+// tile32 = 0: 16-bit tile from a->bc16 (variants 9 / 10); tile32 = 1: fp32 tile from a->bc (variants 11 / 12)
+extern "C" int emu_scan_v9(const cad_scan_fwd_args* a, int G, int pipe, int tile32) {
   using namespace cad;
-  if (a->N != v9::NST || G < 1 || G > v9::kMaxG9 || a->io_dtype == CAD_F32 || !a->bc16 || a->ldbc16 % 64) return -1;
+  if (a->N != v9::NST || G < 1 || G > (tile32 ? v9::kMaxG9 : 7) || a->io_dtype == CAD_F32) return -1;
+  if (tile32 ? (!a->bc || a->ldbc % 32) : (!a->bc16 || a->ldbc16 % 64)) return -1;
   if (a->L <= 0) return 0;
   EmuTmap tmap;
-  tmap.base = a->bc16;
-  tmap.elem_bytes = 2;
+  tmap.base = tile32 ? (const void*)a->bc : a->bc16;
+  tmap.elem_bytes = tile32 ? 4 : 2;
   tmap.nrows = (int64_t)a->njobs * 2 * v9::NST;
-  tmap.ld = a->ldbc16;
-  tmap.nblk = (a->L + 63) / 64;
-  tmap.box_blocks = v9::CH / 64;
+  tmap.ld = tile32 ? a->ldbc : a->ldbc16;
+  const int line = 128 / tmap.elem_bytes;
+  tmap.nblk = (a->L + line - 1) / line;
+  tmap.box_blocks = v9::CH / line;
   tmap.box_rows = 2 * v9::NST;
   const int gx = (int)((a->E + G - 1) / G);
   for (int by = 0; by < a->njobs; ++by)
     for (int bx = 0; bx < gx; ++bx) {
-      if (a->io_dtype == CAD_BF16) run_v9<__nv_bfloat16>(a, &tmap, G, bx, by, pipe);
-      else run_v9<__half>(a, &tmap, G, bx, by, pipe);
+      if (a->io_dtype == CAD_BF16) {
+        if (tile32) run_v9<__nv_bfloat16, float>(a, &tmap, G, bx, by, pipe);
+        else run_v9<__nv_bfloat16, __nv_bfloat16>(a, &tmap, G, bx, by, pipe);
+      } else {
+        if (tile32) run_v9<__half, float>(a, &tmap, G, bx, by, pipe);
+        else run_v9<__half, __half>(a, &tmap, G, bx, by, pipe);
+      }
     }
   return 0;
 }

@@ -36,7 +36,7 @@ def emu():
     lib.emu_scan_v4.restype = C.c_int
     lib.emu_scan_v4.argtypes = [C.POINTER(_lib.ScanFwdArgs), C.c_int]
     lib.emu_scan_v9.restype = C.c_int
-    lib.emu_scan_v9.argtypes = [C.POINTER(_lib.ScanFwdArgs), C.c_int, C.c_int]
+    lib.emu_scan_v9.argtypes = [C.POINTER(_lib.ScanFwdArgs), C.c_int, C.c_int, C.c_int]
     return lib
 
 

@@ -94,25 +94,25 @@ def test_v7_state_outputs_match_v3_fp32():
         assert torch.allclose(got, ref, rtol=2e-4, atol=2e-4 * float(ref.abs().max())), (what, (got - ref).abs().max())
 
 
-# Variants 9 / 10 have passed the CPU emulation of their source (tests/test_emu_scan_v9.py) but the round's GPU budget was
+# Variants 9..12 have passed the CPU emulation of their source (tests/test_emu_scan_v9.py) but the round's GPU budget was
 # spent before their first hardware run: they are opt-in here until that run has happened.
 unmeasured = pytest.mark.skipif(os.environ.get("CAD_RUN_UNMEASURED") != "1",
-                                reason="variants 9 / 10: emulation-verified only; set CAD_RUN_UNMEASURED=1 to run on hardware")
+                                reason="variants 9..12: emulation-verified only; set CAD_RUN_UNMEASURED=1 to run on hardware")
 
 
 @unmeasured
-@pytest.mark.parametrize("variant", [9, 10])
+@pytest.mark.parametrize("variant", [9, 10, 11, 12])
 @pytest.mark.parametrize("L", [1, 17, 513, 2300])
 @pytest.mark.parametrize("rev", [0, 1])
-def test_v9_v10_vs_boundary_restatement(L, rev, variant):
+def test_v9_to_v12_vs_boundary_restatement(L, rev, variant):
     got, ref = _run(L, 64, [(0, 0, rev)], torch.bfloat16, 0, 300 + L, variant)
     _check(got, ref, torch.bfloat16, f"v{variant} L={L} rev={rev}")
 
 
 @unmeasured
-@pytest.mark.parametrize("variant", [9, 10])
+@pytest.mark.parametrize("variant", [9, 10, 11, 12])
 @pytest.mark.parametrize("rev", [0, 1])
-def test_v9_v10_hooks_vs_boundary_restatement(rev, variant):
+def test_v9_to_v12_hooks_vs_boundary_restatement(rev, variant):
     """conv halo + carry-in; end state, sum dt and saved chunk states; then the state-only pass."""
     from caduceus_b200 import functional as CF
     L, E, dtype = 1700, 40, torch.float16
@@ -145,7 +145,8 @@ def test_v4_rejects_what_it_does_not_cover():
                     tuple(d(t) for t in tabs), 100, variant=4)
 
 
-@pytest.mark.parametrize("variant", [4, pytest.param(9, marks=unmeasured), pytest.param(10, marks=unmeasured)])
+@pytest.mark.parametrize("variant", [4, pytest.param(9, marks=unmeasured), pytest.param(10, marks=unmeasured),
+                                     pytest.param(12, marks=unmeasured)])
 @pytest.mark.parametrize("tag", ["ps_small", "ph_config0"])
 def test_model_forward_with_scan_variant_vs_reference_fixture(tag, variant):
     """The whole model with the scan forced to a non-default variant (9 / 10 take their 16-bit tile straight from the
