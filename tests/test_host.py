@@ -154,3 +154,33 @@ def test_hf_save_pretrained_roundtrip(tmp_path, rcps):
     assert isinstance(backbone, caduceus.Caduceus)
     bsd = backbone.state_dict()
     assert all(torch.equal(bsd[k], sd1["caduceus." + k]) for k in bsd)
+
+
+def test_argument_marshalling_and_validation_reach_the_library_without_a_gpu(monkeypatch):
+    """Every forward-scan variant and the conv_xproj call marshal their argument blocks through ctypes, pass the
+    library's own validation and fail LOUDLY at the first CUDA call when there is no device (no fallback); bad
+    arguments are rejected by the library before that."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from caduceus_b200 import functional as CF
+    from scan_boundary_ref import _problem
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    monkeypatch.setattr(CF, "_stream", lambda: None)
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(100, 64, [(0, 0, 0)], torch.bfloat16, 0)
+    packed = (conv_w4, conv_b, dt_b, A2, Dk)
+    for v in (0, 3, 7, 9, 10, 11, 12, 4):
+        with pytest.raises(RuntimeError, match="cad_bimamba_scan_fwd failed .*cuTensorMapEncodeTiled"):
+            CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=v)
+    with pytest.raises(RuntimeError, match="variant must be"):
+        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=5)
+    with pytest.raises(RuntimeError, match="variant 4 needs"):
+        CF.scan_fwd(xz.float(), delta.float(), bc, packed, tuple(tabs), 100, variant=4)
+    with pytest.raises(RuntimeError, match="16-bit I/O"):
+        CF.scan_fwd(xz.float(), delta.float(), bc, packed, tuple(tabs), 100, variant=9)
+    with pytest.raises(RuntimeError, match="bc16"):
+        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=9, bc16=torch.zeros(1, 32, 120, dtype=torch.bfloat16))
+    w_x, w_dt = torch.randn(1, 48, 64).bfloat16(), torch.randn(1, 64, 16).bfloat16()
+    for want in (False, True):
+        with pytest.raises(RuntimeError, match="cad_conv_xproj_fwd failed"):
+            CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, tuple(tabs), 100, want_bc16=want)
