@@ -71,3 +71,31 @@ def test_variant_embeddings_plumbing_matches_reference_loop(rcps):
         r_ref, r_alt = m(rc(ref)).last_hidden_state.flip(dims=[1]), m(rc(alt)).last_hidden_state.flip(dims=[1])
     assert torch.allclose(out["concat_avg_ws"], R.extract_embeddings(f_ref, f_alt, vi), rtol=1e-5, atol=1e-6)
     assert torch.allclose(out["rc_concat_avg_ws"], R.extract_embeddings(r_ref, r_alt, vi), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_variant_embeddings_on_the_cuda_backbone():
+    """The real (rcps) backbone on cuda: the batched ref+alt forward and the in-place RC windows against separate
+    forwards pooled by the oracle restatement."""
+    import caduceus
+    from conftest import golden
+    fx = golden("model_ps_small.pt")
+    cfg = caduceus.CaduceusConfig(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in fx["config"].items()})
+    lm = caduceus.CaduceusForMaskedLM(cfg)
+    lm.load_state_dict(fx["state_dict"])
+    backbone = lm.caduceus.to("cuda").eval()
+    torch.manual_seed(0)
+    B, L = 2, 3000
+    ref = torch.randint(7, 11, (B, L), device="cuda")
+    alt = ref.clone()
+    alt[:, L // 2] = (alt[:, L // 2] - 7 + 1) % 4 + 7
+    out = V.variant_embeddings(backbone, ref, alt, rcps=True)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        o_ref, o_alt = backbone(ref).last_hidden_state, backbone(alt).last_hidden_state
+    vi = torch.full((B,), L // 2, device="cuda")
+    f_ref, r_ref = R.strand_views_rcps(o_ref)
+    f_alt, r_alt = R.strand_views_rcps(o_alt)
+    for key, want in (("concat_avg_ws", R.extract_embeddings(f_ref, f_alt, vi)),
+                      ("rc_concat_avg_ws", R.extract_embeddings(r_ref, r_alt, vi))):
+        assert out[key].shape == (B, 2 * cfg.d_model)
+        assert torch.allclose(out[key].float(), want.float(), rtol=3e-3, atol=5e-3), (key, (out[key] - want).abs().max())
