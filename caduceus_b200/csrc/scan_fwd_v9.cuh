@@ -245,11 +245,15 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
     float2 avA[NP], avB[NP];
     compute_a(0, avA);                                     // independent of the tile: overlaps the TMA wait
     mbar_wait(&sm.bar[buf], parity);
+    // the prefetch is unconditional inside the loop (straight-line code, so the exp2 interleave with the shuffle rounds);
+    // the last pair of states is peeled because state NST-1 has nothing to prefetch
 #pragma unroll 1
-    for (int n = 0; n < NST; n += 2) {
+    for (int n = 0; n < NST - 2; n += 2) {
       run_state(n, avA, avB, true);
-      run_state(n + 1, avB, avA, n + 2 < NST);
+      run_state(n + 1, avB, avA, true);
     }
+    run_state(NST - 2, avA, avB, true);
+    run_state(NST - 1, avB, avA, false);
   } else {
     mbar_wait(&sm.bar[buf], parity);
 #pragma unroll 1
