@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcaduceus_b200.so")
 
 CAD_F32, CAD_F16, CAD_BF16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -82,7 +82,8 @@ class ScanBwdArgs(C.Structure):
                 ("L", _i64), ("E", _i64), ("N", _i64), ("K", _i64),
                 ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64), ("lddz", _i64), ("lddu", _i64),
                 ("lddd", _i64),
-                ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32)]
+                ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
+                ("variant", _i32)]
 
 
 class ConvBwdArgs(C.Structure):

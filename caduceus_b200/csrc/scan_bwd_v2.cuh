@@ -1,0 +1,490 @@
+// Fused bidirectional selective-scan BACKWARD, variant 2 (sm_100a) — same contract as scan_bwd.cu
+// (cad_bimamba_scan_bwd: replaces upstream selective_scan_cuda.bwd, SURVEY.md row A16, reached through autograd of
+// ref:caduceus/modeling_caduceus.py:128-137), rebuilt for thread-level parallelism: the round-1 captures show the
+// scan kernels are latency-bound at the register-file limit, and v1 of the backward (255 registers, one 7-warp CTA per
+// SM, 46 instructions per element) has half the forward's warps to hide twice its dependent chains.
+//
+//   * lane = 8 tokens, pass = 256 tokens.  Each saved 512-token chunk is processed as two halves, second half first;
+//     the state at the midpoint is recomputed by a state-only pass over the first half (one extra exp2 per element of
+//     that half).  All per-token arrays halve, so the kernel fits 128 registers and TWO CTAs per SM (14 warps).
+//   * adjoint carried as ehat_t = a_t e_t (the gradient w.r.t. the state ENTERING token t):
+//         e_t = C_t dy_t + ehat_{t+1},   ehat_t = a_t e_t
+//     so the suffix scan over lanes uses the SAME segment decay prod(a) as the forward scan (no "a of the next token",
+//     no second exp2 of a shifted sum), the chunk-to-chunk adjoint carry IS dL/dh at the boundary (= dhlast / dh0 of
+//     the sharding hooks), and  e_t h_{t-1} a_t = ehat_t h_{t-1}  saves a multiply in the dA / d dt terms.
+//   * dA2 is accumulated per lane in shared memory and reduced once per kernel, not with 5 shuffles per state.
+//   * dB / dC: per-state shared-memory slots (conflict-free 16-byte pieces), summed over the CTA's channels and added
+//     with red.global.add.v4.f32 as in v1.
+// Written against the SIMT primitives of scan_fwd_v4/v9.cuh so that tests/emu/ compiles THIS file for the host.
+#pragma once
+#include "scan_fwd_v9.cuh"
+
+namespace cad {
+namespace bw2 {
+
+#ifndef CAD_EMULATE
+CAD_DEV float shfl_down1(float v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+template <int OFF>
+CAD_DEV void scan_step_dn1(float& Q, float& E, int lane) { scan_step_down<OFF>(Q, E, lane); }
+CAD_DEV void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+CAD_DEV void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+CAD_DEV void atomic_add_f32(float* addr, float v) { atomicAdd(addr, v); }
+#endif
+
+using v9::shfl_up1; using v9::shfl_idx1; using v9::shfl_xor1; using v9::scan_step1; using v9::warp_sync;
+using v4::cta_sync; using v4::tmap_t;
+
+constexpr int TOK = 8;              // tokens per lane
+constexpr int HALF = 32 * TOK;      // 256 tokens per pass
+constexpr int CH = 2 * HALF;        // 512 tokens per saved chunk (the forward's chunk_state granularity)
+constexpr int NST = 16;
+constexpr int kMaxG = 7;
+constexpr int kTileBytes = 2 * NST * CH * 4;     // fp32 B/C tile of one chunk
+constexpr float kLn2f = 0.6931471805599453f;
+
+struct Smem {
+  uint32_t tile;      // 2N x 512 fp32 (TMA, SWIZZLE_128B)
+  uint32_t slots;     // [2][G][2][HALF] fp32: dB / dC contributions of the current state, per warp
+  uint32_t cin;       // [G][NST] state at the start of the current chunk
+  uint32_t mid;       // [G][NST] state at the midpoint of the current chunk
+  uint32_t ecar;      // [G][NST] ehat at the first token of what was processed last (dL/dh at that boundary)
+  uint32_t a2;        // [G][NST]
+  uint32_t dA2;       // [G][NST][32] per-lane partial sums
+  uint64_t* bar;
+  unsigned char* base;
+};
+
+CAD_DEV float sigmoid_fast(float v) { return rcp(1.0f + ex2(-kLog2e * v)); }
+
+// 8 consecutive elements of the io dtype at a 16-byte aligned address -> fp32
+template <typename T>
+CAD_DEV void load8(const T* p, float (&v)[TOK]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = io<T>::to_f(e[k]);
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 q = *reinterpret_cast<const float4*>(p + 4 * h);
+      v[4 * h] = q.x; v[4 * h + 1] = q.y; v[4 * h + 2] = q.z; v[4 * h + 3] = q.w;
+    }
+  }
+}
+template <typename T>
+CAD_DEV void store8(T* p, const float (&v)[TOK]) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 raw;
+    T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = io<T>::from_f(v[k]);
+    *reinterpret_cast<uint4*>(p) = raw;
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      *reinterpret_cast<float4*>(p + 4 * h) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+  }
+}
+
+// slot addressing: the lane's two 16-byte pieces, XOR-swizzled so that a quarter-warp's 128 bytes hit 32 distinct banks
+CAD_DEV int slot_piece(int seg, int k) { return seg * 2 + (k ^ ((seg >> 2) & 1)); }
+
+struct Ctx {
+  int lane, seg, warp, G;
+  bool active;
+  uint32_t a2_s, cin_s, mid_s, ecar_s, dA2_s;
+  float cw[4], cb, dtb, Dk;
+};
+
+// u = silu(conv(x)) and dt = softplus(dt_raw + b) of this lane's 8 tokens of the pass starting at physical token hstart
+// (logical order; masked tokens t >= L: x by the halo rule, dt = 0).
+template <typename T, bool REV, typename XAT>
+CAD_DEV void prologue(const Ctx& cx, const T* __restrict__ xrow, const T* __restrict__ drow, int64_t hstart, int64_t tseg,
+                      int64_t L, const float (&hal)[3], XAT x_at, float (&u)[TOK], float (&dt)[TOK], float& dsum) {
+  auto phys = [](int i) { return REV ? TOK - 1 - i : i; };
+  auto halo_at = [&](int64_t tau) { return tau == -1 ? hal[2] : (tau == -2 ? hal[1] : (tau == -3 ? hal[0] : 0.f)); };
+  float xs[TOK], dr[TOK];
+  if (tseg < L) {
+    load8<T>(xrow + tseg, xs);
+    load8<T>(drow + tseg, dr);
+  } else {
+#pragma unroll
+    for (int i = 0; i < TOK; ++i) { xs[i] = 0.f; dr[i] = 0.f; }
+  }
+  float xl[TOK + 3];
+#pragma unroll
+  for (int i = 0; i < TOK; ++i) {
+    float v = xs[phys(i)];
+    const int64_t t = tseg + phys(i);
+    if (t >= L) v = REV ? halo_at(L - 1 - t) : 0.f;
+    xl[i + 3] = v;
+  }
+  // logical predecessors: previous lane, or (lane 0) the 3 tokens physically adjacent to this pass
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+  if (cx.lane == 0) {
+    const int64_t tb = REV ? hstart + HALF + 2 : hstart - 3;
+    p0 = x_at(tb);
+    p1 = x_at(REV ? tb - 1 : tb + 1);
+    p2 = x_at(REV ? tb - 2 : tb + 2);
+  }
+  const float u0 = shfl_up1(xl[TOK + 0], 1), u1 = shfl_up1(xl[TOK + 1], 1), u2 = shfl_up1(xl[TOK + 2], 1);
+  xl[0] = cx.lane == 0 ? p0 : u0;
+  xl[1] = cx.lane == 0 ? p1 : u1;
+  xl[2] = cx.lane == 0 ? p2 : u2;
+  dsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < TOK; ++i) {
+    u[i] = silu_io<T>(cx.cb + cx.cw[0] * xl[i] + cx.cw[1] * xl[i + 1] + cx.cw[2] * xl[i + 2] + cx.cw[3] * xl[i + 3]);
+    const float raw = dr[phys(i)] + cx.dtb;
+    float d = softplus(raw);
+    if (tseg + phys(i) >= L) d = 0.f;
+    dt[i] = d;
+    dsum += d;
+  }
+}
+
+// this lane's two 16-byte pieces of tile row `row` for the pass with physical half index hp
+CAD_DEV void tile_pieces(uint32_t tile_s, int row, int hp, int seg, float (&v)[TOK]) {
+  const int line = hp * 8 + (seg >> 2), c0 = 2 * (seg & 3);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 q = lds128(tile_s + row * (CH * 4) + line * 128 + (((c0 + k) ^ (line & 7)) << 4));
+    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+  }
+}
+
+template <typename T, bool REV>
+CAD_DEV void run_job(const cad_scan_bwd_args& a, const tmap_t* tmap, int job, int seq, int pset, const Smem& sm) {
+  Ctx cx;
+  cx.lane = CAD_TID & 31;
+  cx.warp = CAD_TID >> 5;
+  cx.G = CAD_NTHREADS >> 5;
+  const int lane = cx.lane, warp = cx.warp, G = cx.G;
+  const int64_t L = a.L, E = a.E;
+  const int64_t chn = (int64_t)CAD_BIDX * G + warp;
+  cx.active = chn < E;
+  const int64_t chc = cx.active ? chn : E - 1;
+  const int64_t nchunks = (L + CH - 1) / CH;
+  auto phys = [](int i) { return REV ? TOK - 1 - i : i; };
+
+  const T* __restrict__ xrow = static_cast<const T*>(a.xz) + ((int64_t)seq * 2 * E + chc) * a.ldxz;
+  const T* __restrict__ zrow = xrow + E * a.ldxz;
+  const T* __restrict__ drow = static_cast<const T*>(a.delta) + ((int64_t)job * E + chc) * a.ldd;
+  const T* __restrict__ gorow = static_cast<const T*>(a.dout) + ((int64_t)job * E + chc) * a.ldo;
+  T* __restrict__ dzrow = static_cast<T*>(a.dz) + ((int64_t)job * E + chc) * a.lddz;
+  T* __restrict__ durow = static_cast<T*>(a.du) + ((int64_t)job * E + chc) * a.lddu;
+  T* __restrict__ ddrow = static_cast<T*>(a.ddelta) + ((int64_t)job * E + chc) * a.lddd;
+
+  const int64_t pc = (int64_t)pset * E + chc;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cx.cw[k] = a.conv_w[pc * 4 + k];
+  cx.cb = a.conv_b[pc]; cx.dtb = a.dt_b[pc]; cx.Dk = a.Dskip[pc];
+  cx.a2_s = sm.a2 + warp * (NST * 4);
+  cx.cin_s = sm.cin + warp * (NST * 4);
+  cx.mid_s = sm.mid + warp * (NST * 4);
+  cx.ecar_s = sm.ecar + warp * (NST * 4);
+  cx.dA2_s = sm.dA2 + warp * (NST * 32 * 4);
+  if (lane < NST) {
+    sts32(cx.a2_s + 4 * lane, a.A2[pc * NST + lane]);
+    // adjoint carry-in: dL/d(state after the last token) when a later shard consumes it (sequence sharding)
+    sts32(cx.ecar_s + 4 * lane, (a.dhlast && cx.active) ? a.dhlast[((int64_t)job * E + chc) * NST + lane] : 0.f);
+  }
+#pragma unroll
+  for (int n = 0; n < NST; ++n) sts32(cx.dA2_s + (n * 32 + lane) * 4, 0.f);
+  float hal[3] = {0.f, 0.f, 0.f};
+  if (a.halo) {
+    const T* hp = static_cast<const T*>(a.halo) + ((int64_t)job * E + chc) * 3;
+    hal[0] = io<T>::to_f(hp[0]); hal[1] = io<T>::to_f(hp[1]); hal[2] = io<T>::to_f(hp[2]);
+  }
+  // x at PHYSICAL time t, with the out-of-sequence rule of the forward (halo before logical 0, zero elsewhere)
+  auto x_at = [&](int64_t t) -> float {
+    if (t >= 0 && t < L) return io<T>::to_f(xrow[t]);
+    const int64_t tau = REV ? L - 1 - t : t;
+    return tau == -1 ? hal[2] : (tau == -2 ? hal[1] : (tau == -3 ? hal[0] : 0.f));
+  };
+
+  cx.seg = REV ? 31 - lane : lane;
+  const int seg = cx.seg;
+  const int job_row = job * 2 * NST;
+  constexpr int BPC = CH / kBlkTok;
+  const int nthreads = CAD_NTHREADS;
+  float dD_acc = 0.f, ddtb_acc = 0.f;
+
+  cta_sync();
+  if (CAD_TID == 0) {
+    const int64_t first_pc = REV ? 0 : nchunks - 1;                  // physical index of the logically LAST chunk
+    mbar_expect_tx(sm.bar, kTileBytes);
+    tma_load_3d(sm.base, tmap, 0, (int)(first_pc * BPC), job_row, sm.bar);
+  }
+
+  uint32_t parity = 0;
+  for (int64_t c = nchunks - 1; c >= 0; --c) {
+    const int64_t pcidx = REV ? nchunks - 1 - c : c;
+    // ---- state at the start of this chunk ------------------------------------------------------------------------
+    if (lane < NST) {
+      float v = 0.f;
+      if (c > 0) v = a.chunk_state[(((int64_t)job * E + chc) * nchunks + (c - 1)) * NST + lane];
+      else if (a.h0) v = a.h0[((int64_t)job * E + chc) * NST + lane];
+      sts32(cx.cin_s + 4 * lane, v);
+    }
+    warp_sync();
+    mbar_wait(sm.bar, parity);
+    parity ^= 1;
+    const int hp0 = REV ? 1 : 0;                                     // physical half holding the logically FIRST 256 tokens
+
+    // ---- pass 0: state at the midpoint (state-only forward over the logically first half) ---------------------------
+    {
+      const int64_t hstart = pcidx * CH + (int64_t)hp0 * HALF, tseg = hstart + (int64_t)seg * TOK;
+      float u[TOK], dt[TOK], dsum;
+      prologue<T, REV>(cx, xrow, drow, hstart, tseg, L, hal, x_at, u, dt, dsum);
+#pragma unroll 1
+      for (int n = 0; n < NST; ++n) {
+        const float A2n = lds32(cx.a2_s + 4 * n), cin = lds32(cx.cin_s + 4 * n);
+        float brow[TOK];
+        tile_pieces(sm.tile, n, hp0, seg, brow);
+        float hl = (lane == 0) ? cin : 0.f;
+#pragma unroll
+        for (int i = 0; i < TOK; ++i) hl = fmaf(ex2(dt[i] * A2n), hl, dt[i] * u[i] * brow[phys(i)]);
+        float P = ex2(A2n * dsum);
+        scan_step1<1>(P, hl, lane);
+        scan_step1<2>(P, hl, lane);
+        scan_step1<4>(P, hl, lane);
+        scan_step1<8>(P, hl, lane);
+        scan_step1<16>(P, hl, lane);
+        if (lane == 31) sts32(cx.mid_s + 4 * n, hl);
+      }
+      warp_sync();
+    }
+
+    // ---- passes 1, 2: backward over the second half (from the midpoint state), then over the first (from cin) ------
+#pragma unroll 1
+    for (int pass = 1; pass >= 0; --pass) {
+      const int hp = pass ? 1 - hp0 : hp0;
+      const uint32_t start_s = pass ? cx.mid_s : cx.cin_s;
+      const int64_t hstart = pcidx * CH + (int64_t)hp * HALF, tseg = hstart + (int64_t)seg * TOK;
+      const bool seg_in = tseg < L;
+      float u[TOK], dt[TOK], dy[TOK], dsum;
+      prologue<T, REV>(cx, xrow, drow, hstart, tseg, L, hal, x_at, u, dt, dsum);
+      {
+        float gs[TOK], zs[TOK];
+        if (seg_in) { load8<T>(gorow + tseg, gs); load8<T>(zrow + tseg, zs); }
+        else {
+#pragma unroll
+          for (int i = 0; i < TOK; ++i) { gs[i] = 0.f; zs[i] = 0.f; }
+        }
+#pragma unroll
+        for (int i = 0; i < TOK; ++i)
+          dy[i] = (tseg + phys(i) >= L || !cx.active) ? 0.f : gs[phys(i)] * silu_io<T>(zs[phys(i)]);   // idle warps add zeros
+      }
+      // live across the state loop: dt, dtu = dt u, dy and four accumulators per token
+      //   y = sum_n C h,  ddt = sum_n ehat h_prev A ln2,  gB = sum_n e B   (d dt += gB u,  d u += gB dt  afterwards)
+      float ddt[TOK], gB[TOK], y[TOK], dtu[TOK];
+#pragma unroll
+      for (int i = 0; i < TOK; ++i) { ddt[i] = 0.f; gB[i] = 0.f; y[i] = 0.f; dD_acc += dy[i] * u[i]; dtu[i] = dt[i] * u[i]; }
+
+#pragma unroll 1
+      for (int n = 0; n < NST; ++n) {
+        const float A2n = lds32(cx.a2_s + 4 * n);
+        const float hstart_n = lds32(start_s + 4 * n);
+        const float ecar = lds32(cx.ecar_s + 4 * n);
+        float av[TOK], hs[TOK], beta[TOK], brow[TOK];
+        float hin;
+        // ---------- forward recompute: h_t of this pass ------------------------------------------------------------
+        tile_pieces(sm.tile, n, hp, seg, brow);
+        {
+          float bv[TOK];
+          float hl = (lane == 0) ? hstart_n : 0.f;
+#pragma unroll
+          for (int i = 0; i < TOK; ++i) {
+            av[i] = ex2(dt[i] * A2n);
+            bv[i] = dtu[i] * brow[phys(i)];
+            hl = fmaf(av[i], hl, bv[i]);
+          }
+          float P = ex2(A2n * dsum);
+          scan_step1<1>(P, hl, lane);
+          scan_step1<2>(P, hl, lane);
+          scan_step1<4>(P, hl, lane);
+          scan_step1<8>(P, hl, lane);
+          scan_step1<16>(P, hl, lane);
+          hin = shfl_up1(hl, 1);
+          if (lane == 0) hin = hstart_n;
+          float h = hin;
+#pragma unroll
+          for (int i = 0; i < TOK; ++i) { h = fmaf(av[i], h, bv[i]); hs[i] = h; }
+        }
+        {
+          float cv[TOK];
+          tile_pieces(sm.tile, NST + n, hp, seg, cv);
+#pragma unroll
+          for (int i = 0; i < TOK; ++i) {
+            y[i] = fmaf(cv[phys(i)], hs[i], y[i]);
+            beta[i] = cv[phys(i)] * dy[i];
+          }
+        }
+        // ---------- adjoint: ehat_i = a_i (beta_i + ehat_{i+1}), suffix scan over lanes with the forward's decay ------
+        float el = (lane == 31) ? ecar : 0.f;
+#pragma unroll
+        for (int i = TOK - 1; i >= 0; --i) el = fmaf(av[i], el, av[i] * beta[i]);   // one FFMA on the dependent chain
+        float Q = ex2(A2n * dsum);
+        bw2::scan_step_dn1<1>(Q, el, lane);
+        bw2::scan_step_dn1<2>(Q, el, lane);
+        bw2::scan_step_dn1<4>(Q, el, lane);
+        bw2::scan_step_dn1<8>(Q, el, lane);
+        bw2::scan_step_dn1<16>(Q, el, lane);
+        float ex = shfl_down1(el, 1);                              // ehat entering my segment from the right
+        if (lane == 31) ex = ecar;
+        warp_sync();
+        if (lane == 0) sts32(cx.ecar_s + 4 * n, el);               // dL/dh at the first token of this pass
+        // ---------- gradients, walking the segment backwards -----------------------------------------------------
+        float dA2n = 0.f;
+        const float A2ln2 = A2n * kLn2f;
+        float dBv[TOK], dCv[TOK];
+#pragma unroll
+        for (int i = TOK - 1; i >= 0; --i) {
+          const float e = beta[i] + ex;                            // e_i
+          ex = av[i] * e;                                          // ehat_i
+          const float hprev = (i == 0) ? hin : hs[i - 1];
+          const float t2 = ex * hprev;
+          dA2n = fmaf(t2, dt[i], dA2n);
+          ddt[i] = fmaf(t2, A2ln2, ddt[i]);
+          gB[i] = fmaf(e, brow[phys(i)], gB[i]);
+          dBv[phys(i)] = e * dtu[i];                               // idle warps: dy = 0 and ecar = 0, hence e = 0
+          dCv[phys(i)] = dy[i] * hs[i];
+        }
+        {
+          const uint32_t da = cx.dA2_s + (n * 32 + lane) * 4;
+          sts32(da, lds32(da) + dA2n);
+        }
+        // ---------- dB / dC: sum over this CTA's channels, then one vector RED per 4 tokens -------------------------
+        const uint32_t slot = sm.slots + (uint32_t)(((n & 1) * G + warp) * (2 * HALF) * 4);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          sts128f(slot + slot_piece(seg, k) * 16, dBv[4 * k], dBv[4 * k + 1], dBv[4 * k + 2], dBv[4 * k + 3]);
+          sts128f(slot + HALF * 4 + slot_piece(seg, k) * 16, dCv[4 * k], dCv[4 * k + 1], dCv[4 * k + 2], dCv[4 * k + 3]);
+        }
+        cta_sync();
+        {
+          const uint32_t sbase = sm.slots + (uint32_t)((n & 1) * G * (2 * HALF) * 4);
+          for (int q = CAD_TID; q < 2 * (HALF / 4); q += nthreads) {
+            const int row = q / (HALF / 4), p4 = q - row * (HALF / 4);          // p4: swizzled piece index
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t pbase = sbase + (uint32_t)(row * HALF * 4 + p4 * 16);
+#pragma unroll
+            for (int w = 0; w < kMaxG; ++w)                                     // constant offsets; G is CTA-uniform
+              if (w < G) {
+                const float4 v = lds128(pbase + (uint32_t)(w * 2 * HALF * 4));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+              }
+            const int sg2 = p4 >> 1, k = (p4 & 1) ^ ((sg2 >> 2) & 1);            // un-swizzle
+            const int64_t t = hstart + sg2 * TOK + 4 * k;
+            if (t < L) red_add_v4(a.dbc + ((int64_t)job_row + row * NST + n) * a.ldbc + t, acc);   // pads get zeros only
+          }
+        }
+      }
+
+      // ---------- per-token outputs of this pass: dz, d dt_raw, du ------------------------------------------------------
+      if (seg_in && cx.active) {
+        float gs[TOK], zs[TOK], dr[TOK], o_dz[TOK], o_dd[TOK], o_du[TOK];
+        load8<T>(gorow + tseg, gs);
+        load8<T>(zrow + tseg, zs);
+        load8<T>(drow + tseg, dr);
+#pragma unroll
+        for (int i = 0; i < TOK; ++i) {
+          const float zz = zs[phys(i)];
+          const float s = sigmoid_fast(zz);
+          o_dz[phys(i)] = gs[phys(i)] * fmaf(cx.Dk, u[i], y[i]) * s * (1.0f + zz * (1.0f - s));
+          const float raw = dr[phys(i)] + cx.dtb;                  // d softplus / d dt_raw, recomputed (not kept live)
+          const float sgd = raw > 20.0f ? 1.0f : sigmoid_fast(raw);
+          const float dd = fmaf(gB[i], u[i], ddt[i]) * sgd;
+          o_dd[phys(i)] = dd;
+          if (tseg + phys(i) < L) ddtb_acc += dd;
+          o_du[phys(i)] = fmaf(gB[i], dt[i], dy[i] * cx.Dk);
+        }
+        if (tseg + TOK <= L) {
+          store8<T>(dzrow + tseg, o_dz);
+          store8<T>(ddrow + tseg, o_dd);
+          store8<T>(durow + tseg, o_du);
+        } else {
+#pragma unroll
+          for (int i = 0; i < TOK; ++i)
+            if (tseg + i < L) {
+              dzrow[tseg + i] = io<T>::from_f(o_dz[i]);
+              ddrow[tseg + i] = io<T>::from_f(o_dd[i]);
+              durow[tseg + i] = io<T>::from_f(o_du[i]);
+            }
+        }
+      }
+      warp_sync();
+    }
+
+    if (c == 0 && a.dh0 && cx.active && lane < NST)
+      a.dh0[((int64_t)job * E + chn) * NST + lane] = lds32(cx.ecar_s + 4 * lane);
+
+    // ---- tile hand-over and request of the logically previous chunk --------------------------------------------------
+    cta_sync();
+    if (c > 0 && CAD_TID == 0) {
+      const int64_t npc = REV ? pcidx + 1 : pcidx - 1;
+      mbar_expect_tx(sm.bar, kTileBytes);
+      tma_load_3d(sm.base, tmap, 0, (int)(npc * BPC), job_row, sm.bar);
+    }
+  }
+
+  // ---- per-channel parameter gradients ----------------------------------------------------------------------------------
+  warp_sync();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dD_acc += shfl_xor1(dD_acc, o);
+    ddtb_acc += shfl_xor1(ddtb_acc, o);
+  }
+  if (cx.active) {
+    if (lane == 0) {
+      atomic_add_f32(a.dDskip + pc, dD_acc);
+      atomic_add_f32(a.ddt_b + pc, ddtb_acc);
+    }
+    if (lane < NST) {
+      float s = 0.f;
+      for (int l = 0; l < 32; ++l) s += lds32(cx.dA2_s + (lane * 32 + l) * 4);
+      atomic_add_f32(a.dA2 + pc * NST + lane, s * kLn2f);
+    }
+  }
+}
+
+// shared-memory plan (bytes from the 1024-aligned base): tile | slots | cin | mid | ecar | a2 | dA2 partials | bar
+CAD_DEV void carve(unsigned char* base, Smem& sm) {
+  const uint32_t b = smem_u32(base);
+  sm.base = base;
+  sm.tile = b;
+  sm.slots = b + kTileBytes;
+  sm.cin = sm.slots + 2 * kMaxG * 2 * HALF * 4;
+  sm.mid = sm.cin + kMaxG * NST * 4;
+  sm.ecar = sm.mid + kMaxG * NST * 4;
+  sm.a2 = sm.ecar + kMaxG * NST * 4;
+  sm.dA2 = sm.a2 + kMaxG * NST * 4;
+  sm.bar = reinterpret_cast<uint64_t*>(base + kTileBytes + 2 * kMaxG * 2 * HALF * 4 + 4 * kMaxG * NST * 4 +
+                                       kMaxG * NST * 32 * 4);
+}
+inline size_t smem_bytes() {
+  return 1024 + (size_t)kTileBytes + (size_t)2 * kMaxG * 2 * HALF * 4 + (size_t)4 * kMaxG * NST * 4 +
+         (size_t)kMaxG * NST * 32 * 4 + 16;
+}
+
+template <typename T>
+CAD_DEV void kernel_body(const cad_scan_bwd_args& a, const tmap_t* tmap, unsigned char* smem_raw) {
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Smem sm;
+  carve(base, sm);
+  if (CAD_TID == 0) mbar_init(sm.bar, 1);
+  const int job = CAD_BIDY;
+  const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
+  if (rev) run_job<T, true>(a, tmap, job, seq, pset, sm);
+  else     run_job<T, false>(a, tmap, job, seq, pset, sm);
+}
+
+}  // namespace bw2
+}  // namespace cad

@@ -16,6 +16,7 @@ _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
 SCAN_TOKENS_PER_LANE = 0   # 0 = library default; 8 / 16 force the scan's tokens per lane (tuning knob)
 SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7 / 9..12: see cad_scan_fwd_args.variant
+SCAN_BWD_VARIANT = int(__import__("os").environ.get("CAD_SCAN_BWD_VARIANT", "0"))   # 0 = library default; 1 / 2: see cad_scan_bwd_args.variant
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
 
@@ -406,9 +407,10 @@ def conv_halo_grad(xz, du_total, halo, conv_w4, conv_b, jobs, L):
 
 
 def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None, want_dh0=False,
-             channels_per_cta=0, dhlast=None):
+             channels_per_cta=0, dhlast=None, variant=None):
     """Backward of scan_fwd: returns dz, du (scan path), ddelta (io dtype), dbc (fp32), ddt_b, dA2, dD, dh0.
-    `dhlast` (njobs, E, N): gradient w.r.t. the end state, i.e. the adjoint entering from the next shard."""
+    `dhlast` (njobs, E, N): gradient w.r.t. the end state, i.e. the adjoint entering from the next shard.
+    `variant`: cad_scan_bwd_args.variant (None = SCAN_BWD_VARIANT / CAD_SCAN_BWD_VARIANT, 0 = library default)."""
     lib = _lib.load()
     seq, pset, rev = jobs
     conv_w4, conv_b, dt_b, A2, Dk = packed
@@ -433,7 +435,7 @@ def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None
         _ptr(dz), _ptr(du), _ptr(ddelta), _ptr(dbc), _ptr(ddt_b), _ptr(dA2), _ptr(dD), _ptr(dh0),
         _ptr(dhlast),
         L, E, N, 4, ldxz, delta.stride(1), ldbc, dout.stride(1), ldxz, ldxz, ldxz,
-        nseq, njobs, P, _dt(xz), channels_per_cta)
+        nseq, njobs, P, _dt(xz), channels_per_cta, SCAN_BWD_VARIANT if variant is None else int(variant))
     _lib.check(lib.cad_bimamba_scan_bwd(C.byref(a), _stream()), "cad_bimamba_scan_bwd")
     _launched()
     return dz, du, ddelta, dbc, ddt_b, dA2, dD, dh0

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CAD_ABI_VERSION 2
+#define CAD_ABI_VERSION 3
 
 typedef enum { CAD_F32 = 0, CAD_F16 = 1, CAD_BF16 = 2 } cad_dtype;
 
@@ -211,6 +211,9 @@ typedef struct {
   int64_t L, E, N, K;
   int64_t ldxz, ldd, ldbc, ldo, lddz, lddu, lddd;
   int32_t nseq, njobs, npset, io_dtype, channels_per_cta;
+  int32_t variant;          /* 0 = library default (1); 1 = 16 tokens per lane, one 512-token pass per saved chunk
+                               (255 registers, one CTA per SM); 2 = 8 tokens per lane, two 256-token passes per saved
+                               chunk with the midpoint state recomputed (128 registers, two CTAs per SM) */
 } cad_scan_bwd_args;
 int cad_bimamba_scan_bwd(const cad_scan_bwd_args* a, void* stream);
 

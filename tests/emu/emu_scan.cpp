@@ -8,6 +8,7 @@
 #include "simt_emu.h"
 #include "../../caduceus_b200/csrc/scan_fwd_v4.cuh"
 #include "../../caduceus_b200/csrc/scan_fwd_v9.cuh"
+#include "../../caduceus_b200/csrc/scan_bwd_v2.cuh"
 
 namespace cad {
 thread_local EmuThread g_t;
@@ -99,6 +100,29 @@ extern "C" int emu_scan_v9(const cad_scan_fwd_args* a, int G, int pipe, int tile
         if (tile32) run_v9<__half, float>(a, &tmap, G, bx, by, pipe);
         else run_v9<__half, __half>(a, &tmap, G, bx, by, pipe);
       }
+    }
+  return 0;
+}
+
+extern "C" int emu_scan_bwd_v2(const cad_scan_bwd_args* a, int G) {
+  using namespace cad;
+  if (a->N != bw2::NST || G < 1 || G > bw2::kMaxG || a->ldbc % 32) return -1;
+  if (a->L <= 0) return 0;
+  EmuTmap tmap;
+  tmap.base = a->bc;
+  tmap.elem_bytes = 4;
+  tmap.nrows = (int64_t)a->njobs * 2 * bw2::NST;
+  tmap.ld = a->ldbc;
+  tmap.nblk = (a->L + 31) / 32;
+  tmap.box_blocks = bw2::CH / 32;
+  tmap.box_rows = 2 * bw2::NST;
+  const int gx = (int)((a->E + G - 1) / G);
+  const size_t sb = bw2::smem_bytes();
+  for (int by = 0; by < a->njobs; ++by)
+    for (int bx = 0; bx < gx; ++bx) {
+      if (a->io_dtype == CAD_BF16) run_cta(sb, G, bx, by, [&](unsigned char* sm) { bw2::kernel_body<__nv_bfloat16>(*a, &tmap, sm); });
+      else if (a->io_dtype == CAD_F16) run_cta(sb, G, bx, by, [&](unsigned char* sm) { bw2::kernel_body<__half>(*a, &tmap, sm); });
+      else run_cta(sb, G, bx, by, [&](unsigned char* sm) { bw2::kernel_body<float>(*a, &tmap, sm); });
     }
   return 0;
 }

@@ -34,6 +34,10 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kBlkTok = 32;
 
 template <typename T> struct io;
+template <> struct io<float> {
+  static float to_f(float v) { return v; }
+  static float from_f(float v) { return v; }
+};
 template <> struct io<__half> {
   static float to_f(__half v) { return __half2float(v); }
   static __half from_f(float v) { return __float2half_rn(v); }
@@ -221,4 +225,26 @@ inline void scan_step1(float& P, float& H, int lane) {
 }
 inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 }  // namespace v9
+
+namespace bw2 {
+inline float shfl_down1(float v, int off) { const int l = g_t.tid & 31; return v4::shfl_raw(v, l + off < 32 ? l + off : l); }
+template <int OFF>
+inline void scan_step_dn1(float& Q, float& E, int lane) {
+  const float Qn = shfl_down1(Q, OFF), En = shfl_down1(E, OFF);
+  if (lane < 32 - OFF) { E = fmaf(Q, En, E); Q = Q * Qn; }
+}
+inline void sts128f(uint32_t a, float x, float y, float z, float w) {
+  if (a & 15) abort();
+  const float v[4] = {x, y, z, w};
+  memcpy(smem_at(a, 16), v, 16);
+}
+// global atomics: one process-wide mutex (CTAs run one after another, threads of a CTA concurrently)
+inline std::mutex& global_mutex() { static std::mutex m; return m; }
+inline void red_add_v4(float* addr, float4 v) {
+  if ((uintptr_t)addr & 15) { fprintf(stderr, "emu: misaligned red.global.add.v4\n"); abort(); }
+  std::lock_guard<std::mutex> g(global_mutex());
+  addr[0] += v.x; addr[1] += v.y; addr[2] += v.z; addr[3] += v.w;
+}
+inline void atomic_add_f32(float* addr, float v) { std::lock_guard<std::mutex> g(global_mutex()); *addr += v; }
+}  // namespace bw2
 }  // namespace cad

@@ -87,3 +87,63 @@ def _problem(L, E, njobs_spec, dtype, seed):
     return xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc
 
 
+
+
+def boundary_grads(xz, delta, bc, dout, conv_w4, conv_b, dt_b, A2, Dk, seq, pset, rev, L, halo=None, h0=None, dhlast=None,
+                   chunk=512):
+    """float64 autograd of the operator at the kernel boundary = what cad_bimamba_scan_bwd must return
+    (include/caduceus_b200.h): dz, du (w.r.t. u = silu(conv(x)) as an independent input: the conv is differentiated by
+    a separate kernel), ddelta (w.r.t. dt_raw), dbc, ddt_b, dA2, dD, dh0 — for the loss  sum(out * dout) [+ sum(hlast *
+    dhlast)].  Also returns the forward's chunk states (the saved tensor the backward consumes).  torch tensors in."""
+    T = torch.float64
+    njobs, E = delta.shape[0], delta.shape[1]
+    N = bc.shape[1] // 2
+    P = A2.shape[0]
+    nchunks = (L + chunk - 1) // chunk
+    dt_b_l = dt_b.to(T).clone().requires_grad_(True)
+    A2_l = A2.to(T).clone().requires_grad_(True)
+    D_l = Dk.to(T).clone().requires_grad_(True)
+    z_l = [xz[seq[j], E:, :L].to(T).clone().requires_grad_(True) for j in range(njobs)]
+    dr_l = [delta[j, :, :L].to(T).clone().requires_grad_(True) for j in range(njobs)]
+    bc_l = [bc[j, :, :L].to(T).clone().requires_grad_(True) for j in range(njobs)]
+    h0_l = [(torch.zeros(E, N, dtype=T) if h0 is None else h0[j].to(T).clone()).requires_grad_(True) for j in range(njobs)]
+    u_l, loss, cstates = [], 0.0, torch.zeros(njobs, E, nchunks, N, dtype=T)
+    for j in range(njobs):
+        p = pset[j]
+        idx = torch.arange(L - 1, -1, -1) if rev[j] else torch.arange(L)       # logical time -> physical token
+        x = xz[seq[j], :E, :L].to(T)[:, idx]
+        pre = torch.zeros(E, 3, dtype=T) if halo is None else halo[j].to(T)
+        xp = torch.cat([pre, x], dim=1)
+        w = conv_w4[p].to(T)
+        c = conv_b[p].to(T)[:, None] + sum(w[:, k:k + 1] * xp[:, k:k + L] for k in range(4))
+        u = (c * torch.sigmoid(c)).detach().clone().requires_grad_(True)           # logical order
+        u_l.append(u)
+        raw = dr_l[j][:, idx] + dt_b_l[p][:, None]
+        dt = torch.where(raw > 20.0, raw, torch.log1p(torch.exp(torch.clamp(raw, max=20.0))))
+        B, Cm = bc_l[j][:N][:, idx], bc_l[j][N:][:, idx]
+        zz = z_l[j][:, idx]
+        h = h0_l[j]
+        first = L - (nchunks - 1) * chunk if rev[j] else chunk
+        bounds = [min(L, first + cc * chunk) for cc in range(nchunks)]
+        ci, ys = 0, []
+        for t in range(L):
+            h = torch.exp2(dt[:, t:t + 1] * A2_l[p]) * h + (dt[:, t] * u[:, t])[:, None] * B[None, :, t]
+            ys.append((h * Cm[None, :, t]).sum(1) + D_l[p] * u[:, t])
+            while ci < nchunks and t + 1 == bounds[ci]:
+                cstates[j, :, ci] = h.detach()
+                ci += 1
+        y = torch.stack(ys, dim=1)
+        out = y * (zz * torch.sigmoid(zz))
+        loss = loss + (out * dout[j, :, :L].to(T)[:, idx]).sum()
+        if dhlast is not None:
+            loss = loss + (h * dhlast[j].to(T)).sum()
+    loss.backward()
+    zero = lambda t: torch.zeros_like(t) if t.grad is None else t.grad     # noqa: E731
+    inv = lambda j: (torch.arange(L - 1, -1, -1) if rev[j] else torch.arange(L))   # noqa: E731  (self-inverse map)
+    dz = torch.stack([zero(z_l[j]) for j in range(njobs)])
+    ddelta = torch.stack([zero(dr_l[j]) for j in range(njobs)])
+    dbc = torch.stack([zero(bc_l[j]) for j in range(njobs)])
+    du = torch.stack([zero(u_l[j])[:, inv(j)] for j in range(njobs)])              # back to physical order
+    dh0 = torch.stack([zero(h0_l[j]) for j in range(njobs)])
+    return dict(dz=dz, du=du, ddelta=ddelta, dbc=dbc, ddt_b=zero(dt_b_l), dA2=zero(A2_l), dD=zero(D_l), dh0=dh0,
+                chunk_state=cstates)

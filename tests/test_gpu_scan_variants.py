@@ -1,5 +1,6 @@
-"""GPU parity of the non-default forward-scan kernels (cad_scan_fwd_args.variant = 4 paired channels, 7 no replay,
-9 / 10 16-bit tile + barrier-free hand-over), through the C-ABI: against the float64 restatement at the kernel boundary
+"""GPU parity of the non-default scan kernels (cad_scan_fwd_args.variant = 4 paired channels, 7 no replay,
+9 / 10 16-bit tile + barrier-free hand-over, 11 / 12 the same on a shared fp32 tile; cad_scan_bwd_args.variant = 2, the
+two-CTAs-per-SM backward), through the C-ABI: against the float64 restatement at the kernel boundary
 (tests/scan_boundary_ref.py — the same checker the CPU emulation of these kernels is held to), against the default
 kernel (variant 3) on identical inputs, and end to end through the model against the fixture produced by the
 reference's own code."""
@@ -10,7 +11,7 @@ import pytest
 import torch
 
 from conftest import golden, tol
-from scan_boundary_ref import _problem, boundary_ref
+from scan_boundary_ref import _problem, boundary_grads, boundary_ref
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -174,3 +175,94 @@ def test_model_forward_with_scan_variant_vs_reference_fixture(tag, variant):
     scale = fx["logits"].abs().max().item()
     err = (logits - fx["logits"]).abs().max().item()
     assert err <= atol + rtol * scale * 4, (err, scale)
+
+
+# ---- backward variant 2 (csrc/scan_bwd_v2.cuh; CPU emulation: tests/test_emu_scan_bwd_v2.py) ---------------------------
+def _bwd(L, E, spec, dtype, G, seed, variant, hooks=False):
+    from caduceus_b200 import functional as CF
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, seed)
+    njobs, N = len(spec), 16
+    g = torch.Generator().manual_seed(seed + 1)
+    dout = torch.randn(njobs, E, ld, generator=g).to(dtype)
+    halo = h0 = dhlast = None
+    if hooks:
+        halo = torch.randn(njobs, E, 3, generator=g).to(dtype)
+        h0 = torch.randn(njobs, E, N, generator=g)
+        dhlast = torch.randn(njobs, E, N, generator=g)
+    seq, pset, rev = ([s_[k] for s_ in spec] for k in range(3))
+    ref = boundary_grads(xz.float(), delta.float(), bc, dout.float(), conv_w4, conv_b, dt_b, A2, Dk, seq, pset, rev, L,
+                         halo=None if halo is None else halo.float(), h0=h0, dhlast=dhlast)
+    d = lambda t: None if t is None else t.to(DEV).contiguous()   # noqa: E731
+    packed, jobs = tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)), tuple(d(t) for t in tabs)
+    # the saved tensor comes from the forward KERNEL, as in training
+    _, _, _, cstate = CF.scan_fwd(d(xz), d(delta), d(bc), packed, jobs, L, halo=d(halo), h0=d(h0), want_state=True,
+                                  want_chunk_state=True)
+    got = CF.scan_bwd(d(xz), d(delta), d(bc), d(dout), packed, jobs, L, cstate, halo=d(halo), h0=d(h0),
+                      want_dh0=hooks, dhlast=d(dhlast), channels_per_cta=G, variant=variant)
+    torch.cuda.synchronize()
+    names = ("dz", "du", "ddelta", "dbc", "ddt_b", "dA2", "dD", "dh0")
+    return {k: (None if v is None else v.float().cpu()) for k, v in zip(names, got)}, ref
+
+
+def _check_grads(got, ref, L, dtype, what, hooks=False):
+    eps = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11, torch.float32: 0.0}[dtype]
+    for k in ("dz", "du", "ddelta", "dbc", "ddt_b", "dA2", "dD") + (("dh0",) if hooks else ()):
+        g_, r = got[k].double(), ref[k].double()
+        if k in ("dz", "du", "ddelta", "dbc"):
+            g_ = g_[..., :L]
+        assert torch.isfinite(g_).all(), (what, k)
+        scale = max(1.0, float(r.abs().max()))
+        err, bound = (g_ - r).abs(), 2e-3 * scale + (2 * eps + 2e-3) * r.abs()     # MUFU approximations: 2e-3 relative
+        assert torch.all(err <= bound), f"{what} {k}: max err {err.max():.3e} (scale {scale:.3e})"
+
+
+@unmeasured
+@pytest.mark.parametrize("L", [1, 9, 255, 513, 1030, 2300])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_bwd_v2_vs_float64_autograd_at_the_boundary(L, rev):
+    got, ref = _bwd(L, 24, [(0, 0, rev)], torch.float32, 0, 400 + L, 2)
+    _check_grads(got, ref, L, torch.float32, f"bwd v2 L={L} rev={rev}")
+
+
+@unmeasured
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("G", [1, 3, 7])
+def test_bwd_v2_ps_job_layout_hooks_and_cta_shapes(dtype, G):
+    spec = [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0)]
+    got, ref = _bwd(1700, 19, spec, dtype, G, 17, 2, hooks=True)
+    _check_grads(got, ref, 1700, dtype, f"bwd v2 G={G} {dtype}", hooks=True)
+
+
+@unmeasured
+def test_bwd_v2_agrees_with_v1_on_identical_inputs():
+    spec = [(0, 0, 0), (0, 1, 1)]
+    g2, ref = _bwd(5000, 64, spec, torch.float32, 0, 3, 2)
+    g1, _ = _bwd(5000, 64, spec, torch.float32, 0, 3, 1)
+    _check_grads(g1, ref, 5000, torch.float32, "bwd v1")
+    _check_grads(g2, ref, 5000, torch.float32, "bwd v2")
+
+
+@unmeasured
+def test_mixer_backward_with_bwd_v2_vs_oracle_autograd():
+    """BiMambaWrapper.backward with the scan gradient forced to variant 2, against autograd through the CPU oracle."""
+    import caduceus_b200
+    from caduceus_b200 import functional as CF
+    from test_gpu_backward import _grad_close, _oracle_mixer_grads
+    fx = golden("mixer_add_tied.pt")
+    m = caduceus_b200.BiMambaWrapper(fx["d_model"], bidirectional=True, bidirectional_strategy=fx["strategy"],
+                                     bidirectional_weight_tie=fx["tie"], **fx["ssm_cfg"])
+    m.load_state_dict(fx["state_dict"])
+    m = m.to(DEV)
+    torch.manual_seed(0)
+    h, gout = torch.randn(2, 1537, fx["d_model"]), torch.randn(2, 1537, fx["d_model"])
+    hd = h.to(DEV).requires_grad_(True)
+    try:
+        CF.SCAN_BWD_VARIANT = 2
+        m(hd).backward(gout.to(DEV))
+    finally:
+        CF.SCAN_BWD_VARIANT = 0
+    _, ref_dh, ref_dp = _oracle_mixer_grads(fx["state_dict"], h, gout, fx["strategy"])
+    _grad_close(hd.grad, ref_dh, 5e-3, 1e-3, "d hidden")
+    for name, p in m.named_parameters():
+        if ref_dp[name] is not None:
+            _grad_close(p.grad, ref_dp[name].reshape(p.shape), 5e-3, 2e-3, f"d {name}")

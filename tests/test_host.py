@@ -180,6 +180,12 @@ def test_argument_marshalling_and_validation_reach_the_library_without_a_gpu(mon
         CF.scan_fwd(xz.float(), delta.float(), bc, packed, tuple(tabs), 100, variant=9)
     with pytest.raises(RuntimeError, match="bc16"):
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=9, bc16=torch.zeros(1, 32, 120, dtype=torch.bfloat16))
+    cstate = torch.zeros(1, 64, 1, 16)
+    for v in (0, 1, 2):
+        with pytest.raises(RuntimeError, match="cad_bimamba_scan_bwd failed .*cuTensorMapEncodeTiled"):
+            CF.scan_bwd(xz, delta, bc, torch.zeros_like(delta), packed, tuple(tabs), 100, cstate, variant=v)
+    with pytest.raises(RuntimeError, match="unknown variant"):
+        CF.scan_bwd(xz, delta, bc, torch.zeros_like(delta), packed, tuple(tabs), 100, cstate, variant=3)
     w_x, w_dt = torch.randn(1, 48, 64).bfloat16(), torch.randn(1, 64, 16).bfloat16()
     for want in (False, True):
         with pytest.raises(RuntimeError, match="cad_conv_xproj_fwd failed"):
