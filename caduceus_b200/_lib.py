@@ -53,7 +53,7 @@ class ScanFwdArgs(C.Structure):
                 ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
                 ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
                 ("state_only", _i32), ("tokens_per_lane", _i32), ("variant", _i32),
-                ("bc16", _p), ("ldbc16", _i64)]
+                ("bc16", _p), ("ldbc16", _i64), ("delta_is_dt", _i32)]
 
 
 class ScanFixupArgs(C.Structure):
@@ -105,7 +105,7 @@ class ConvXprojArgs(C.Structure):
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
                 ("delta", _p), ("bc", _p),
                 ("L", _i64), ("E", _i64), ("N", _i64), ("R", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64),
-                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bc16", _p), ("ldbc16", _i64)]
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bc16", _p), ("ldbc16", _i64), ("dt_b", _p)]
 
 
 class ConvFwdArgs(C.Structure):

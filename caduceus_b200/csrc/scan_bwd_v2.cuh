@@ -234,7 +234,7 @@ CAD_DEV void run_job(const cad_scan_bwd_args& a, const tmap_t* tmap, int job, in
       sts32(cx.cin_s + 4 * lane, v);
     }
     warp_sync();
-    mbar_wait(sm.bar, parity);
+    mbar_wait_wd(sm.bar, parity);
     parity ^= 1;
     const int hp0 = REV ? 1 : 0;                                     // physical half holding the logically FIRST 256 tokens
 

@@ -32,6 +32,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same wait with a watchdog, for kernels whose hand-over protocol has not yet run on hardware: a barrier that
+// does not complete within 2 s (a whole launch takes milliseconds) traps — the launch fails loudly instead of hanging the GPU
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  uint64_t t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try(bar, parity)) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 2000000000ull) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
                                             uint64_t* bar) {
   asm volatile(

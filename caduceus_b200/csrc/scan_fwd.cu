@@ -526,6 +526,8 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4 || a->variant == 7 || (a->variant >= 9 && a->variant <= 12),
               "cad_bimamba_scan_fwd: variant must be 0, 3, 4, 7 or 9..12");
+  CAD_REQUIRE(!a->delta_is_dt || (a->variant >= 9 && a->io_dtype != CAD_F32 && !a->chunk_state),
+              "cad_bimamba_scan_fwd: delta_is_dt needs variant 9..12, 16-bit I/O and no saved chunk states (inference)");
   if (a->variant == 4) {
     CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
                 "halo / h0 / hlast / dtsum / chunk_state / state_only");

@@ -131,7 +131,8 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
     if (seg_in) {
       cp_wait_all();
       v4::load16<T>(cx.pre_cur + 0 * ROW, xs);
-      v4::load16<T>(cx.pre_cur + 1 * ROW, dr);
+      if (a.delta_is_dt) v4::load16<__half>(cx.pre_cur + 1 * ROW, dr);   // dt itself, fp16 (written by conv_xproj)
+      else v4::load16<T>(cx.pre_cur + 1 * ROW, dr);
     } else {
 #pragma unroll
       for (int i = 0; i < TOK; ++i) { xs[i] = 0.f; dr[i] = 0.f; }
@@ -167,10 +168,17 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
 #pragma unroll
     for (int k = 0; k < 3; ++k) prev3[k] = shfl_idx1(xl[TOK + k], 31);
     float dt[TOK], du[TOK], y[TOK];
+    if (a.delta_is_dt) {                                   // launch-uniform branch: no softplus (2 MUFU per token) here
+#pragma unroll
+      for (int i = 0; i < TOK; ++i) dt[i] = dr[phys(i)];
+    } else {
+#pragma unroll
+      for (int i = 0; i < TOK; ++i) dt[i] = softplus(dr[phys(i)] + pr.y);
+    }
 #pragma unroll
     for (int i = 0; i < TOK; ++i) {
       const float u = silu_io<T>(pr.x + cw.x * xl[i] + cw.y * xl[i + 1] + cw.z * xl[i + 2] + cw.w * xl[i + 3]);
-      float d = softplus(dr[phys(i)] + pr.y);
+      float d = dt[i];
       if (TAIL && tseg + phys(i) >= L) d = 0.f;           // masked token: a = 1, b = 0 -> state passes through
       dt[i] = d;
       dsum += d;
@@ -244,7 +252,7 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
   if (PIPE) {
     float2 avA[NP], avB[NP];
     compute_a(0, avA);                                     // independent of the tile: overlaps the TMA wait
-    mbar_wait(&sm.bar[buf], parity);
+    mbar_wait_wd(&sm.bar[buf], parity);
     // the prefetch is unconditional inside the loop (straight-line code, so the exp2 interleave with the shuffle rounds);
     // the last pair of states is peeled because state NST-1 has nothing to prefetch
 #pragma unroll 1
@@ -255,7 +263,7 @@ CAD_DEV void chunk(const cad_scan_fwd_args& a, const Smem& sm, const ChunkCtx& c
     run_state(NST - 2, avA, avB, true);
     run_state(NST - 1, avB, avA, false);
   } else {
-    mbar_wait(&sm.bar[buf], parity);
+    mbar_wait_wd(&sm.bar[buf], parity);
 #pragma unroll 1
     for (int n = 0; n < NST; ++n) {
       float2 av[NP];

@@ -53,6 +53,8 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 template <typename T>
+__device__ __forceinline__ float round_io(float v) { return io<T>::to_f(io<T>::from_f(v)); }
+template <typename T>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   T v[2] = {io<T>::from_f(lo), io<T>::from_f(hi)};
   return *reinterpret_cast<uint32_t*>(v);
@@ -257,15 +259,26 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
   }
   T* mystg = stg + (size_t)warp * 16 * UP;
   T* __restrict__ dbase = static_cast<T*>(a.delta) + (int64_t)job * E * a.ldd;
+  const bool emit_dt = a.dt_b != nullptr;           // launch-uniform
   for (int64_t mt = warp; mt < E / 16; mt += 8) {
     uint32_t afr[4];
     ldsm_x4(afr, wdts + (16 * mt + (lane & 15)) * DP + 8 * (lane >> 4));
+    float db0 = 0.f, db1 = 0.f;
+    if (emit_dt) { db0 = a.dt_b[(int64_t)pset * E + 16 * mt + g]; db1 = a.dt_b[(int64_t)pset * E + 16 * mt + g + 8]; }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
       mma_t<T>::mma(c, afr, bdt[j]);
-      *reinterpret_cast<uint32_t*>(mystg + g * UP + 8 * j + q2) = pack2<T>(c[0], c[1]);
-      *reinterpret_cast<uint32_t*>(mystg + (g + 8) * UP + 8 * j + q2) = pack2<T>(c[2], c[3]);
+      if (emit_dt) {      // (branch kept inside the loop: the unswitched form costs 12 more registers and spills)
+        // dt = softplus(dt_raw rounded to the io dtype (the reference's rounding point) + bias), stored as fp16
+        *reinterpret_cast<uint32_t*>(mystg + g * UP + 8 * j + q2) =
+            pack2<__half>(softplus(round_io<T>(c[0]) + db0), softplus(round_io<T>(c[1]) + db0));
+        *reinterpret_cast<uint32_t*>(mystg + (g + 8) * UP + 8 * j + q2) =
+            pack2<__half>(softplus(round_io<T>(c[2]) + db1), softplus(round_io<T>(c[3]) + db1));
+      } else {
+        *reinterpret_cast<uint32_t*>(mystg + g * UP + 8 * j + q2) = pack2<T>(c[0], c[1]);
+        *reinterpret_cast<uint32_t*>(mystg + (g + 8) * UP + 8 * j + q2) = pack2<T>(c[2], c[3]);
+      }
     }
     __syncwarp();
 #pragma unroll

@@ -16,6 +16,7 @@ _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
 SCAN_TOKENS_PER_LANE = 0   # 0 = library default; 8 / 16 force the scan's tokens per lane (tuning knob)
 SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7 / 9..12: see cad_scan_fwd_args.variant
+SCAN_DT_IN_XPROJ = __import__("os").environ.get("CAD_DT_IN_XPROJ", "0") == "1"   # variants 9..12: dt = softplus(.) leaves conv_xproj as fp16
 SCAN_BWD_VARIANT = int(__import__("os").environ.get("CAD_SCAN_BWD_VARIANT", "0"))   # 0 = library default; 1 / 2: see cad_scan_bwd_args.variant
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
@@ -254,10 +255,11 @@ def conv_xproj_supported(xz, N, R):
     return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 1024
 
 
-def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=False):
+def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=False, dt_b=None):
     """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores: returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32)
     without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.  want_bc16: also return the
-    B / C rows in the activation dtype (njobs, 2N, ceil64(L)) — the tile source of scan variants 9 / 10."""
+    B / C rows in the activation dtype (njobs, 2N, ceil64(L)) — the tile source of scan variants 9 / 10.
+    dt_b (P, E) fp32: `delta` then holds dt = softplus(dt_raw + dt_b) as FP16 bits (scan_fwd(..., delta_is_dt=True))."""
     lib = _lib.load()
     seq, pset, rev = jobs
     nseq, twoE, ld = xz.shape
@@ -271,7 +273,8 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=Fal
     bc16 = torch.empty(njobs, 2 * N, round_up(max(L, 1), 64), device=xz.device, dtype=xz.dtype) if want_bc16 else None
     a = _lib.ConvXprojArgs(_ptr(xz), _ptr(w_x.contiguous()), _ptr(w_dt.contiguous()), _ptr(conv_w4), _ptr(conv_b),
                            _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(delta), _ptr(bc),
-                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), _ptr(bc16), bc16.stride(1) if want_bc16 else 0)
+                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), _ptr(bc16), bc16.stride(1) if want_bc16 else 0,
+                           _ptr(dt_b))
     _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
     _launched()
     return (delta, bc, bc16) if want_bc16 else (delta, bc)
@@ -290,7 +293,7 @@ def project_dt_bc(xdbl, dt_w_job, L, N):
 
 
 def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
-             channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None, bc16=None):
+             channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None, bc16=None, delta_is_dt=False):
     """Launch the fused bidirectional scan.
     xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld)."""
     lib = _lib.load()
@@ -313,7 +316,7 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
         _ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
         L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only),
-        SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0, None, 0)
+        SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0, None, 0, int(delta_is_dt))
     a.variant = scan_variant(a) if variant is None else int(variant)
     if a.variant in (9, 10):
         # 16-bit copy of the B / C rows for the 16-bit-tile kernels (experimental path: a cast per call until the

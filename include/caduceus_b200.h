@@ -155,6 +155,9 @@ typedef struct {
                                otherwise; channels_per_cta then counts channel PAIRS) */
   const void* bc16;         /* variants 9 / 10 only: (njobs, 2N, ldbc16) B / C rows in the I/O dtype, zeros in [L, ldbc16) */
   int64_t ldbc16;           /* multiple of 64 elements, >= L */
+  int32_t delta_is_dt;      /* variants 9..12, 16-bit I/O, inference only: `delta` holds dt = softplus(dt_raw + dt_b)
+                               itself as FP16 (whatever io_dtype is), written by cad_conv_xproj_fwd with dt_b set: the
+                               scan's prologue then has no softplus (2 of its MUFU ops per token and channel) */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
@@ -247,6 +250,8 @@ typedef struct {
   int64_t ldxz, ldd, ldbc;
   int32_t nseq, njobs, io_dtype;
   void* bc16; int64_t ldbc16;
+  const float* dt_b;        /* optional (NULL): (P, E) dt bias; when set, `delta` receives dt = softplus(round_io(dt_raw)
+                               + dt_b) as FP16 instead of dt_raw in the io dtype (cad_scan_fwd_args.delta_is_dt) */
 } cad_conv_xproj_args;
 int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
 

@@ -118,6 +118,7 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {            // try_wait.p
     abort();
   }
 }
+inline void mbar_wait_wd(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }   // device: the same wait with a watchdog
 inline void tma_load_3d(void* smem_dst, const EmuTmap* t, int c0, int c1, int c2, uint64_t* bar) {
   if (c0 != 0 || (smem_u32(smem_dst) & 1023)) { fprintf(stderr, "emu: bad TMA destination / coordinate\n"); abort(); }
   unsigned char* dst = (unsigned char*)smem_dst;

@@ -17,7 +17,7 @@ def _silu(v):
 
 
 def boundary_ref(xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, seq, pset, rev, L, halo=None, h0=None, full=False,
-                 chunk=512):
+                 chunk=512, delta_is_dt=False):
     """float64 restatement at the kernel boundary.  xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc).
     halo (njobs, E, 3): x at logical times -3, -2, -1; h0 (njobs, E, N): carry-in state.
     full=True also returns (hlast, dtsum, chunk_state) — the state after every `chunk` LOGICAL tokens counted the way
@@ -41,7 +41,7 @@ def boundary_ref(xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, seq, pset, rev, L
         xp = np.concatenate([pre, x], axis=1)
         w = conv_w4[p].astype(np.float64)
         u = _silu(conv_b[p].astype(np.float64)[:, None] + sum(w[:, k:k + 1] * xp[:, k:k + L] for k in range(4)))
-        dt = _softplus(dr + dt_b[p].astype(np.float64)[:, None])
+        dt = dr if delta_is_dt else _softplus(dr + dt_b[p].astype(np.float64)[:, None])   # cad_scan_fwd_args.delta_is_dt
         a2 = A2[p].astype(np.float64)                              # (E, N), already * log2(e)
         h = np.zeros((E, N)) if h0 is None else h0[j].astype(np.float64).copy()
         y = np.zeros((E, L))

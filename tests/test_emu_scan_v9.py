@@ -14,9 +14,14 @@ from scan_boundary_ref import _problem, boundary_ref
 from test_emu_scan_v4 import emu  # noqa: F401  (module-scoped fixture: builds tests/emu/libemu_scan.so)
 
 
-def _run(lib, L, E, spec, dtype, G, seed, pipe, hooks=False, state_only=False, tile32=False):
+def _run(lib, L, E, spec, dtype, G, seed, pipe, hooks=False, state_only=False, tile32=False, dt_ready=False):
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, seed)
     njobs, N = len(spec), 16
+    delta_f = delta.float()
+    if dt_ready:
+        # what cad_conv_xproj_fwd writes when dt_b is set: softplus(dt_raw + bias) as FP16 bits, whatever the io dtype
+        dt16 = torch.nn.functional.softplus(delta.float() + dt_b[tabs[1].long()][:, :, None]).half()
+        delta, delta_f = dt16.view(dtype) if dtype != torch.float16 else dt16, dt16.float()
     g = torch.Generator().manual_seed(seed + 1)
     ld16 = (L + 63) // 64 * 64
     bc16 = torch.zeros(njobs, 2 * N, ld16, dtype=dtype)
@@ -39,12 +44,13 @@ def _run(lib, L, E, spec, dtype, G, seed, pipe, hooks=False, state_only=False, t
                          p(dtsum) if want else None, p(cstate) if hooks and not state_only else None,
                          L, E, N, 4, ld, ld, ldbc, ld, xz.shape[0], njobs, conv_w4.shape[0],
                          _lib.CAD_BF16 if dtype == torch.bfloat16 else _lib.CAD_F16, G, int(state_only), 0,
-                         (12 if pipe else 11) if tile32 else (10 if pipe else 9), None if tile32 else p(bc16), ld16)
+                         (12 if pipe else 11) if tile32 else (10 if pipe else 9), None if tile32 else p(bc16), ld16,
+                         int(dt_ready))
     assert lib.emu_scan_v9(C.byref(a), G, int(pipe), int(tile32)) == 0
     f = lambda t: None if t is None else t.float().numpy()   # noqa: E731
-    ref = boundary_ref(f(xz), f(delta), f(bc16), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk),
+    ref = boundary_ref(f(xz), delta_f.numpy(), f(bc16), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk),
                        [s for s, _, _ in spec], [q for _, q, _ in spec], [r for _, _, r in spec], L,
-                       halo=f(halo), h0=f(h0), full=True)
+                       halo=f(halo), h0=f(h0), full=True, delta_is_dt=dt_ready)
     eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
     if not state_only:
         got = out.float().numpy()
@@ -101,3 +107,12 @@ def test_emulated_v11_fp32_tile_ragged_lengths(emu, L, rev, pipe):   # noqa: F81
 def test_emulated_v12_fp32_tile_wide_cta_with_hooks(emu):   # noqa: F811
     """9 warps in one CTA sharing the fp32 tile (the 14-warp configuration in small), hooks on, four chunks."""
     _run(emu, 1700, E=9, spec=[(0, 0, 0), (0, 0, 1)], dtype=torch.float16, G=9, seed=21, pipe=1, hooks=True, tile32=True)
+
+
+@pytest.mark.parametrize("tile32", [False, True])
+@pytest.mark.parametrize("L,rev", [(513, 0), (1030, 1)])
+def test_emulated_v10_v12_dt_precomputed_by_conv_xproj(emu, L, rev, tile32):   # noqa: F811
+    """cad_scan_fwd_args.delta_is_dt: `delta` holds dt = softplus(dt_raw + b) as fp16 bits under bf16 I/O (what
+    cad_conv_xproj_fwd writes when dt_b is set); the kernel's prologue skips the softplus."""
+    _run(emu, L, E=3, spec=[(0, 0, rev), (0, 1, 1 - rev)], dtype=torch.bfloat16, G=2, seed=810 + L, pipe=1, tile32=tile32,
+         dt_ready=True)

@@ -146,8 +146,34 @@ def test_v4_rejects_what_it_does_not_cover():
                     tuple(d(t) for t in tabs), 100, variant=4)
 
 
+@unmeasured
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_conv_xproj_dt_epilogue_matches_softplus_of_its_own_dt_raw(dtype):
+    """cad_conv_xproj_args.dt_b: the delta rows become dt = softplus(dt_raw + b) as fp16 bits; dt_raw itself (rounded to
+    the io dtype, the reference's rounding point) is what the same kernel writes without dt_b; B / C rows are unchanged."""
+    from caduceus_b200 import functional as CF
+    L, E, R, N = 1500, 128, 8, 16
+    g = torch.Generator().manual_seed(5)
+    xz = torch.randn(2, 2 * E, 1504, generator=g).to(dtype).to(DEV)
+    w_x = (torch.randn(2, R + 2 * N, E, generator=g) * E ** -0.5).to(dtype).to(DEV)
+    w_dt = (torch.randn(2, E, R, generator=g) * R ** -0.5).to(dtype).to(DEV)
+    conv_w4 = (0.5 * torch.randn(2, E, 4, generator=g)).to(DEV)
+    conv_b = (0.1 * torch.randn(2, E, generator=g)).to(DEV)
+    dt_b = (torch.randn(2, E, generator=g) * 2 - 3).to(DEV)
+    dt_b[:, 0] = 25.0
+    jobs = tuple(torch.tensor(v, dtype=torch.int32, device=DEV) for v in ([0, 0, 1, 1], [0, 1, 0, 1], [0, 1, 1, 0]))
+    raw, bc0 = CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L)
+    dt16, bc1 = CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, dt_b=dt_b)
+    assert torch.equal(bc0, bc1)
+    got = (dt16 if dtype == torch.float16 else dt16.view(torch.float16))[..., :L].float()
+    want = torch.nn.functional.softplus(raw[..., :L].float() + dt_b[jobs[1].long()][:, :, None])
+    assert torch.isfinite(got).all()
+    assert torch.allclose(got, want, rtol=2e-3, atol=1e-6), (got - want).abs().max()      # 2 fp16 ulps (MUFU ex2 / lg2)
+
+
 @pytest.mark.parametrize("variant", [4, pytest.param(9, marks=unmeasured), pytest.param(10, marks=unmeasured),
-                                     pytest.param(12, marks=unmeasured)])
+                                     pytest.param(12, marks=unmeasured), pytest.param(-10, marks=unmeasured),
+                                     pytest.param(-12, marks=unmeasured)])
 @pytest.mark.parametrize("tag", ["ps_small", "ph_config0"])
 def test_model_forward_with_scan_variant_vs_reference_fixture(tag, variant):
     """The whole model with the scan forced to a non-default variant (9 / 10 take their 16-bit tile straight from the
@@ -161,13 +187,16 @@ def test_model_forward_with_scan_variant_vs_reference_fixture(tag, variant):
     model = model.to(DEV).to(torch.bfloat16).eval()
     launches = []
     orig = CF.scan_variant
+    dt_in_xproj, variant = variant < 0, abs(variant)      # negative: softplus moved into conv_xproj (CAD_DT_IN_XPROJ)
     try:
+        CF.SCAN_DT_IN_XPROJ = dt_in_xproj
         CF.SCAN_VARIANT = variant
         CF.scan_variant = lambda a: launches.append(orig(a)) or launches[-1]
         with torch.no_grad():
             logits = model(fx["input_ids"].to(DEV)).logits.float().cpu()
     finally:
         CF.SCAN_VARIANT = 0
+        CF.SCAN_DT_IN_XPROJ = False
         CF.scan_variant = orig
     assert launches and all(v == variant for v in launches), launches
     # same criterion as test_gpu_parity.py::test_model_low_precision_vs_reference_fixture (16-bit stack vs fp32 fixture)

@@ -189,4 +189,8 @@ def test_argument_marshalling_and_validation_reach_the_library_without_a_gpu(mon
     w_x, w_dt = torch.randn(1, 48, 64).bfloat16(), torch.randn(1, 64, 16).bfloat16()
     for want in (False, True):
         with pytest.raises(RuntimeError, match="cad_conv_xproj_fwd failed"):
-            CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, tuple(tabs), 100, want_bc16=want)
+            CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, tuple(tabs), 100, want_bc16=want, dt_b=dt_b if want else None)
+    with pytest.raises(RuntimeError, match="delta_is_dt needs variant 9..12"):
+        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=3, delta_is_dt=True)
+    with pytest.raises(RuntimeError, match="cad_bimamba_scan_fwd failed .*cuTensorMapEncodeTiled"):
+        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=12, delta_is_dt=True)
