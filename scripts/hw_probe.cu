@@ -1,0 +1,347 @@
+// Python-free hardware probe of the scan kernels through the C-ABI (seconds, not minutes: no interpreter / torch start-up).
+// For the kernels that were built and CPU-verified after a round's GPU budget ran out:
+//   group A (forward, Caduceus-PS headline shape: 4 jobs x 512 channels x 131072 tokens, bf16 I/O):
+//     every forward variant against variant 3 on identical device-generated inputs (max |diff| / max |ref|, NaN count)
+//     and its launch time (CUDA events, min / mean of 5 after 2 warm-ups); variants 10 / 12 also with dt precomputed
+//   group B (backward, Caduceus-Ph shape: 2 jobs): variant 2 against variant 1 on every gradient, and both times.
+//   group C (conv_xproj): the optional bc16 / dt outputs against the plain outputs of the same kernel, and both times.
+// Each group runs in its own process (fork before any CUDA call) so that a trap in one kernel cannot take the other
+// group's results with it; every line is flushed to gpurun_out/hw_probe.log as soon as it is known.
+//
+//   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I include scripts/hw_probe.cu -o scripts/_bin/hw_probe \
+//        -L caduceus_b200/csrc -lcaduceus_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../caduceus_b200/csrc'
+//   ./scripts/_bin/hw_probe [L]
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <vector>
+
+#include "caduceus_b200.h"
+
+static FILE* g_log = nullptr;
+static double now_s() { timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
+static double g_t0 = 0;
+static void say(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  printf("[%6.2fs] %s\n", now_s() - g_t0, buf); fflush(stdout);
+  if (g_log) { fprintf(g_log, "[%6.2fs] %s\n", now_s() - g_t0, buf); fflush(g_log); }
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { say("CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
+
+__device__ __forceinline__ uint32_t hash32(uint64_t i, uint32_t seed) {
+  uint64_t z = i + 0x9E3779B97F4A7C15ull * (seed + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+  return (uint32_t)z;
+}
+__device__ __forceinline__ float urand(uint64_t i, uint32_t seed, float lo, float hi) {
+  return lo + (hi - lo) * (hash32(i, seed) >> 8) * (1.0f / 16777216.0f);
+}
+__global__ void fill_bf16(__nv_bfloat16* p, int64_t n, uint32_t seed, float lo, float hi) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = __float2bfloat16_rn(urand(i, seed, lo, hi));
+}
+__global__ void bf16_to_f32(const __nv_bfloat16* s, float* d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+// dt16[j, c, t] = half(softplus(float(delta[j, c, t]) + dt_b[pset[j], c]))   — what conv_xproj writes when dt_b is set
+__global__ void make_dt16(const __nv_bfloat16* delta, const float* dt_b, const int32_t* pset, __half* dt16, int64_t E,
+                          int64_t ld, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / ld, j = row / E, c = row - j * E;
+    const float v = __bfloat162float(delta[i]) + dt_b[(int64_t)pset[j] * E + c];
+    dt16[i] = __float2half_rn(v > 20.f ? v : log1pf(expf(v)));
+  }
+}
+// stats[0] = max |a - b|, stats[1] = max |b|, stats[2] = number of non-finite a   (bits of non-negative floats order as uints)
+template <typename T> __device__ __forceinline__ float tof(T v);
+template <> __device__ __forceinline__ float tof<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float tof<float>(float v) { return v; }
+template <> __device__ __forceinline__ float tof<__half>(__half v) { return __half2float(v); }
+__global__ void f32_to_bf16(const float* s, __nv_bfloat16* d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = __float2bfloat16_rn(s[i]);
+}
+template <typename T>
+__global__ void compare(const T* a, const T* b, int64_t n, uint32_t* stats) {
+  float md = 0.f, mr = 0.f; uint32_t bad = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = tof<T>(a[i]), y = tof<T>(b[i]);
+    if (!isfinite(x)) { ++bad; continue; }
+    md = fmaxf(md, fabsf(x - y)); mr = fmaxf(mr, fabsf(y));
+  }
+  atomicMax(stats + 0, __float_as_uint(md)); atomicMax(stats + 1, __float_as_uint(mr));
+  if (bad) atomicAdd(stats + 2, bad);
+}
+
+struct Cmp { float maxdiff, maxref; uint32_t bad; };
+template <typename T>
+static int cmp(const T* a, const T* b, int64_t n, uint32_t* d_stats, Cmp* out) {
+  CK(cudaMemset(d_stats, 0, 12));
+  compare<T><<<1184, 256>>>(a, b, n, d_stats);
+  uint32_t h[3];
+  CK(cudaMemcpy(h, d_stats, 12, cudaMemcpyDeviceToHost));
+  memcpy(&out->maxdiff, &h[0], 4); memcpy(&out->maxref, &h[1], 4); out->bad = h[2];
+  return 0;
+}
+
+struct Problem {
+  int64_t L, E = 512, N = 16;
+  int njobs, nseq, npset = 2;
+  __nv_bfloat16 *xz, *delta, *bc16, *out_ref, *out_var;
+  __half* dt16;
+  float *bc, *conv_w, *conv_b, *dt_b, *A2, *Dk;
+  int32_t *seq, *pset, *rev;
+  uint32_t* stats;
+};
+
+static int make_problem(Problem& p, int64_t L, int njobs) {
+  p.L = L; p.njobs = njobs; p.nseq = njobs / 2;
+  const int64_t E = p.E, N = p.N;
+  CK(cudaMalloc(&p.xz, (size_t)p.nseq * 2 * E * L * 2));
+  CK(cudaMalloc(&p.delta, (size_t)njobs * E * L * 2));
+  CK(cudaMalloc(&p.dt16, (size_t)njobs * E * L * 2));
+  CK(cudaMalloc(&p.bc16, (size_t)njobs * 2 * N * L * 2));
+  CK(cudaMalloc(&p.bc, (size_t)njobs * 2 * N * L * 4));
+  CK(cudaMalloc(&p.out_ref, (size_t)njobs * E * L * 2));
+  CK(cudaMalloc(&p.out_var, (size_t)njobs * E * L * 2));
+  CK(cudaMalloc(&p.stats, 64));
+  // parameter sets (host side, tiny): dt in [1e-3, 0.1] log-uniform at raw = 0, A = -(n+1) * U(0.5, 1.5)
+  std::vector<float> cw(2 * E * 4), cb(2 * E), db(2 * E), a2(2 * E * N), dk(2 * E);
+  uint32_t s = 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (s >> 8) * (1.0f / 16777216.0f); };
+  for (auto& v : cw) v = rnd() - 0.5f;
+  for (auto& v : cb) v = 0.2f * rnd() - 0.1f;
+  for (auto& v : db) { const float dt0 = expf(logf(1e-3f) + rnd() * (logf(0.1f) - logf(1e-3f))); v = logf(expm1f(dt0)); }
+  for (int64_t c = 0; c < 2 * E; ++c) { const float sc = 0.5f + rnd(); for (int n = 0; n < N; ++n) a2[c * N + n] = -(n + 1) * sc * 1.4426950408889634f; }
+  for (auto& v : dk) v = 2.f * rnd() - 1.f;
+  CK(cudaMalloc(&p.conv_w, cw.size() * 4)); CK(cudaMemcpy(p.conv_w, cw.data(), cw.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p.conv_b, cb.size() * 4)); CK(cudaMemcpy(p.conv_b, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p.dt_b, db.size() * 4));   CK(cudaMemcpy(p.dt_b, db.data(), db.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p.A2, a2.size() * 4));     CK(cudaMemcpy(p.A2, a2.data(), a2.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p.Dk, dk.size() * 4));     CK(cudaMemcpy(p.Dk, dk.data(), dk.size() * 4, cudaMemcpyHostToDevice));
+  // job tables: Caduceus-PS order (sequence = strand, rev = direction XOR strand); the first two jobs are Caduceus-Ph
+  const int32_t seq[4] = {0, 0, 1, 1}, pset[4] = {0, 1, 0, 1}, rev[4] = {0, 1, 1, 0};
+  CK(cudaMalloc(&p.seq, 16)); CK(cudaMemcpy(p.seq, seq, 16, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p.pset, 16)); CK(cudaMemcpy(p.pset, pset, 16, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&p.rev, 16)); CK(cudaMemcpy(p.rev, rev, 16, cudaMemcpyHostToDevice));
+  fill_bf16<<<1184, 256>>>(p.xz, (int64_t)p.nseq * 2 * E * L, 1, -1.5f, 1.5f);
+  fill_bf16<<<1184, 256>>>(p.delta, (int64_t)njobs * E * L, 2, -1.5f, 1.5f);
+  fill_bf16<<<1184, 256>>>(p.bc16, (int64_t)njobs * 2 * N * L, 3, -1.5f, 1.5f);
+  bf16_to_f32<<<1184, 256>>>(p.bc16, p.bc, (int64_t)njobs * 2 * N * L);
+  make_dt16<<<1184, 256>>>(p.delta, p.dt_b, p.pset, p.dt16, E, L, (int64_t)njobs * E * L);
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+static cad_scan_fwd_args fwd_args(const Problem& p, int variant, bool dt_ready, __nv_bfloat16* out) {
+  cad_scan_fwd_args a;
+  memset(&a, 0, sizeof a);
+  a.xz = p.xz; a.delta = dt_ready ? (const void*)p.dt16 : (const void*)p.delta; a.bc = p.bc; a.out = out;
+  a.conv_w = p.conv_w; a.conv_b = p.conv_b; a.dt_b = p.dt_b; a.A2 = p.A2; a.Dskip = p.Dk;
+  a.seq_of_job = p.seq; a.pset_of_job = p.pset; a.rev_of_job = p.rev;
+  a.L = p.L; a.E = p.E; a.N = p.N; a.K = 4;
+  a.ldxz = p.L; a.ldd = p.L; a.ldbc = p.L; a.ldo = p.L;
+  a.nseq = p.nseq; a.njobs = p.njobs; a.npset = p.npset; a.io_dtype = CAD_BF16;
+  a.variant = variant; a.bc16 = p.bc16; a.ldbc16 = p.L; a.delta_is_dt = dt_ready ? 1 : 0;
+  return a;
+}
+
+template <typename F>
+static int time_launches(F launch, int warm, int iters, float* t_min, float* t_mean) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < warm; ++i) if (launch()) return 1;
+  CK(cudaDeviceSynchronize());
+  float mn = 1e30f, sum = 0.f;
+  for (int i = 0; i < iters; ++i) {
+    CK(cudaEventRecord(e0, 0));
+    if (launch()) return 1;
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    mn = fminf(mn, ms); sum += ms;
+  }
+  *t_min = mn; *t_mean = sum / iters;
+  return 0;
+}
+
+static int group_forward(int64_t L) {
+  CK(cudaFree(0));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  say("A: device %s, %d SMs, cad ABI v%d", prop.name, prop.multiProcessorCount, cad_version());
+  Problem p;
+  if (make_problem(p, L, 4)) return 1;
+  say("A: inputs ready (PS shape: 4 jobs x %lld channels x %lld tokens, bf16)", (long long)p.E, (long long)L);
+  const int64_t n_out = (int64_t)p.njobs * p.E * L;
+  struct V { int variant; bool dt; const char* name; };
+  const V vs[] = {{3, false, "v3 (default)"}, {12, false, "v12 fp32 tile, 14 warps, pipe"}, {10, false, "v10 16-bit tile, pipe"},
+                  {11, false, "v11 fp32 tile, 14 warps"}, {9, false, "v9 16-bit tile"}, {7, false, "v7 no replay"},
+                  {12, true, "v12 + dt from conv_xproj"}, {10, true, "v10 + dt from conv_xproj"}, {4, false, "v4 paired channels"}};
+  for (const V& v : vs) {
+    __nv_bfloat16* out = v.variant == 3 ? p.out_ref : p.out_var;
+    cad_scan_fwd_args a = fwd_args(p, v.variant, v.dt, out);
+    CK(cudaMemset(out, 0xFF, (size_t)n_out * 2));                    // NaN pattern: unwritten outputs show up
+    int rc = cad_bimamba_scan_fwd(&a, nullptr);
+    if (rc) { say("A: %-32s launch rc %d: %s", v.name, rc, cad_last_error()); if (rc > 0) return 1; continue; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { say("A: %-32s FAILED at run time: %s", v.name, cudaGetErrorString(e)); return 1; }
+    Cmp c;
+    if (cmp<__nv_bfloat16>(out, p.out_ref, n_out, p.stats, &c)) return 1;
+    float tmin, tmean;
+    if (time_launches([&]() { int r = cad_bimamba_scan_fwd(&a, nullptr); if (r) say("launch rc %d", r); return r; }, 2, 5, &tmin, &tmean)) return 1;
+    say("A: %-32s max|diff vs v3| %.3e  max|ref| %.3e  non-finite %u   time min %.3f ms mean %.3f ms", v.name, c.maxdiff,
+        c.maxref, c.bad, tmin, tmean);
+  }
+  // Caduceus-Ph shape = the first two jobs (one sequence, two directions)
+  p.njobs = 2; p.nseq = 1;
+  for (const V& v : vs) {
+    if (v.dt) continue;
+    cad_scan_fwd_args a = fwd_args(p, v.variant, false, p.out_var);
+    float tmin, tmean;
+    const int rc = cad_bimamba_scan_fwd(&a, nullptr);
+    if (rc) { say("A: Ph shape %-23s launch rc %d: %s", v.name, rc, cad_last_error()); if (rc > 0) return 1; continue; }
+    if (time_launches([&]() { return cad_bimamba_scan_fwd(&a, nullptr); }, 1, 5, &tmin, &tmean)) return 1;
+    say("A: Ph shape %-23s time min %.3f ms mean %.3f ms", v.name, tmin, tmean);
+  }
+  return 0;
+}
+
+static int group_backward(int64_t L) {
+  CK(cudaFree(0));
+  Problem p;
+  if (make_problem(p, L, 2)) return 1;
+  const int64_t E = p.E, N = p.N, nch = (L + 511) / 512, n_tok = (int64_t)p.njobs * E * L;
+  float* cstate; CK(cudaMalloc(&cstate, (size_t)p.njobs * E * nch * N * 4));
+  cad_scan_fwd_args f = fwd_args(p, 3, false, p.out_ref);
+  f.chunk_state = cstate;
+  int rc = cad_bimamba_scan_fwd(&f, nullptr);
+  if (rc) { say("B: forward rc %d: %s", rc, cad_last_error()); return 1; }
+  __nv_bfloat16* dout = p.out_var;                                     // reuse: random upstream gradient
+  fill_bf16<<<1184, 256>>>(dout, n_tok, 9, -1.f, 1.f);
+  CK(cudaDeviceSynchronize());
+  say("B: inputs + saved chunk states ready (Ph shape: 2 jobs x %lld channels x %lld tokens)", (long long)E, (long long)L);
+  struct Out { __nv_bfloat16 *dz, *du, *dd; float *dbc, *ddt_b, *dA2, *dD; } o[2];
+  for (int k = 0; k < 2; ++k) {
+    CK(cudaMalloc(&o[k].dz, (size_t)n_tok * 2)); CK(cudaMalloc(&o[k].du, (size_t)n_tok * 2)); CK(cudaMalloc(&o[k].dd, (size_t)n_tok * 2));
+    CK(cudaMalloc(&o[k].dbc, (size_t)p.njobs * 2 * N * L * 4));
+    CK(cudaMalloc(&o[k].ddt_b, 2 * E * 4)); CK(cudaMalloc(&o[k].dA2, 2 * E * N * 4)); CK(cudaMalloc(&o[k].dD, 2 * E * 4));
+  }
+  for (int k = 0; k < 2; ++k) {
+    const int variant = k + 1;
+    cad_scan_bwd_args a;
+    memset(&a, 0, sizeof a);
+    a.xz = p.xz; a.delta = p.delta; a.bc = p.bc; a.dout = dout;
+    a.conv_w = p.conv_w; a.conv_b = p.conv_b; a.dt_b = p.dt_b; a.A2 = p.A2; a.Dskip = p.Dk;
+    a.seq_of_job = p.seq; a.pset_of_job = p.pset; a.rev_of_job = p.rev; a.chunk_state = cstate;
+    a.dz = o[k].dz; a.du = o[k].du; a.ddelta = o[k].dd; a.dbc = o[k].dbc; a.ddt_b = o[k].ddt_b; a.dA2 = o[k].dA2; a.dDskip = o[k].dD;
+    a.L = L; a.E = E; a.N = N; a.K = 4;
+    a.ldxz = L; a.ldd = L; a.ldbc = L; a.ldo = L; a.lddz = L; a.lddu = L; a.lddd = L;
+    a.nseq = p.nseq; a.njobs = p.njobs; a.npset = p.npset; a.io_dtype = CAD_BF16; a.variant = variant;
+    auto zero = [&]() {
+      cudaMemsetAsync(o[k].dbc, 0, (size_t)p.njobs * 2 * N * L * 4); cudaMemsetAsync(o[k].ddt_b, 0, 2 * E * 4);
+      cudaMemsetAsync(o[k].dA2, 0, 2 * E * N * 4); cudaMemsetAsync(o[k].dD, 0, 2 * E * 4);
+    };
+    float tmin, tmean;
+    if (time_launches([&]() { int r = cad_bimamba_scan_bwd(&a, nullptr); if (r) say("B: bwd v%d rc %d: %s", variant, r, cad_last_error()); return r; },
+                      1, 4, &tmin, &tmean)) return 1;
+    zero();                                                            // the kept result: exactly one accumulation
+    CK(cudaMemset(o[k].dz, 0xFF, (size_t)n_tok * 2)); CK(cudaMemset(o[k].du, 0xFF, (size_t)n_tok * 2)); CK(cudaMemset(o[k].dd, 0xFF, (size_t)n_tok * 2));
+    if (cad_bimamba_scan_bwd(&a, nullptr)) return 1;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { say("B: bwd v%d FAILED at run time: %s", variant, cudaGetErrorString(e)); return 1; }
+    say("B: backward variant %d   time min %.3f ms mean %.3f ms", variant, tmin, tmean);
+  }
+  Cmp c;
+  if (cmp<__nv_bfloat16>(o[1].dz, o[0].dz, n_tok, p.stats, &c)) return 1;
+  say("B: v2 vs v1  dz      max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<__nv_bfloat16>(o[1].du, o[0].du, n_tok, p.stats, &c)) return 1;
+  say("B: v2 vs v1  du      max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<__nv_bfloat16>(o[1].dd, o[0].dd, n_tok, p.stats, &c)) return 1;
+  say("B: v2 vs v1  ddelta  max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<float>(o[1].dbc, o[0].dbc, (int64_t)p.njobs * 2 * N * L, p.stats, &c)) return 1;
+  say("B: v2 vs v1  dbc     max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<float>(o[1].ddt_b, o[0].ddt_b, 2 * E, p.stats, &c)) return 1;
+  say("B: v2 vs v1  ddt_b   max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<float>(o[1].dA2, o[0].dA2, 2 * E * N, p.stats, &c)) return 1;
+  say("B: v2 vs v1  dA2     max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<float>(o[1].dD, o[0].dD, 2 * E, p.stats, &c)) return 1;
+  say("B: v2 vs v1  dD      max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  return 0;
+}
+
+// group C: conv_xproj's optional outputs (bc16 = the B / C rows in the io dtype; dt = softplus(dt_raw + b) as fp16)
+static int group_xproj(int64_t L) {
+  CK(cudaFree(0));
+  Problem p;
+  if (make_problem(p, L, 4)) return 1;
+  const int64_t E = p.E, N = p.N, R = 16, n_tok = (int64_t)p.njobs * E * L, n_bc = (int64_t)p.njobs * 2 * N * L;
+  __nv_bfloat16 *w_x, *w_dt, *bc16_ref = p.out_ref;      // out_ref / out_var are free here (n_tok >= n_bc elements)
+  float* bc_b; __half* dt_ref = reinterpret_cast<__half*>(p.out_var);
+  __nv_bfloat16 *delta_b;
+  CK(cudaMalloc(&w_x, 2 * (R + 2 * N) * E * 2)); CK(cudaMalloc(&w_dt, 2 * E * R * 2));
+  CK(cudaMalloc(&bc_b, (size_t)n_bc * 4)); CK(cudaMalloc(&delta_b, (size_t)n_tok * 2));
+  fill_bf16<<<64, 256>>>(w_x, 2 * (R + 2 * N) * E, 21, -0.08f, 0.08f);
+  fill_bf16<<<64, 256>>>(w_dt, 2 * E * R, 22, -0.4f, 0.4f);
+  cad_conv_xproj_args a;
+  memset(&a, 0, sizeof a);
+  a.xz = p.xz; a.w_x = w_x; a.w_dt = w_dt; a.conv_w = p.conv_w; a.conv_b = p.conv_b;
+  a.seq_of_job = p.seq; a.pset_of_job = p.pset; a.rev_of_job = p.rev;
+  a.delta = p.delta; a.bc = p.bc; a.L = L; a.E = E; a.N = N; a.R = R; a.ldxz = L; a.ldd = L; a.ldbc = L;
+  a.nseq = p.nseq; a.njobs = p.njobs; a.io_dtype = CAD_BF16;
+  int rc = cad_conv_xproj_fwd(&a, nullptr);                           // plain: delta = dt_raw (bf16), bc fp32
+  if (rc) { say("C: conv_xproj rc %d: %s", rc, cad_last_error()); return 1; }
+  CK(cudaDeviceSynchronize());
+  make_dt16<<<1184, 256>>>(p.delta, p.dt_b, p.pset, dt_ref, E, L, n_tok);
+  f32_to_bf16<<<1184, 256>>>(p.bc, bc16_ref, n_bc);
+  cad_conv_xproj_args b = a;
+  b.delta = delta_b; b.bc = bc_b; b.bc16 = p.bc16; b.ldbc16 = L; b.dt_b = p.dt_b;
+  CK(cudaMemset(delta_b, 0xFF, (size_t)n_tok * 2)); CK(cudaMemset(p.bc16, 0xFF, (size_t)n_bc * 2));
+  rc = cad_conv_xproj_fwd(&b, nullptr);
+  if (rc) { say("C: conv_xproj (bc16 + dt) rc %d: %s", rc, cad_last_error()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { say("C: conv_xproj (bc16 + dt) FAILED at run time: %s", cudaGetErrorString(e)); return 1; }
+  Cmp c;
+  if (cmp<float>(bc_b, p.bc, n_bc, p.stats, &c)) return 1;
+  say("C: bc (fp32) with vs without the optional outputs   max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<__nv_bfloat16>(p.bc16, bc16_ref, n_bc, p.stats, &c)) return 1;
+  say("C: bc16 vs bf16(bc)                                 max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  if (cmp<__half>(reinterpret_cast<__half*>(delta_b), dt_ref, n_tok, p.stats, &c)) return 1;
+  say("C: dt (fp16) vs softplus(dt_raw + b)                max|diff| %.3e  max|ref| %.3e  non-finite %u", c.maxdiff, c.maxref, c.bad);
+  float t0, t0m, t1, t1m;
+  if (time_launches([&]() { return cad_conv_xproj_fwd(&a, nullptr); }, 1, 4, &t0, &t0m)) return 1;
+  if (time_launches([&]() { return cad_conv_xproj_fwd(&b, nullptr); }, 1, 4, &t1, &t1m)) return 1;
+  say("C: conv_xproj time  plain min %.3f mean %.3f ms;  + bc16 + dt min %.3f mean %.3f ms", t0, t0m, t1, t1m);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  g_t0 = now_s();
+  const int64_t L = argc > 1 ? atoll(argv[1]) : 131072;
+  const char* only = argc > 2 ? argv[2] : "ABC";
+  if (system("mkdir -p gpurun_out") != 0) return 2;
+  g_log = fopen("gpurun_out/hw_probe.log", "a");
+  say("hw_probe: L = %lld, groups %s", (long long)L, only);
+  int status = 0;
+  for (const char* g = only; *g; ++g) {
+    fflush(stdout); if (g_log) fflush(g_log);
+    const pid_t pid = fork();                       // before any CUDA call in this process
+    if (pid == 0) { const int r = (*g == 'A') ? group_forward(L) : (*g == 'B') ? group_backward(L) : group_xproj(L); fflush(stdout); _exit(r); }
+    int st = 0;
+    waitpid(pid, &st, 0);
+    say("group %c finished: %s %d", *g, WIFEXITED(st) ? "exit" : "signal", WIFEXITED(st) ? WEXITSTATUS(st) : WTERMSIG(st));
+    status |= st;
+  }
+  return status ? 1 : 0;
+}
