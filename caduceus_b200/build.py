@@ -73,6 +73,28 @@ def build(force=False, verbose=False):
     return LIB
 
 
+PROBE_SRC = os.path.join(os.path.dirname(HERE), "scripts", "hw_probe.cu")
+PROBE_BIN = os.path.join(os.path.dirname(HERE), "scripts", "_bin", "hw_probe")
+
+
+def build_probe(force=False):
+    """Compile scripts/hw_probe.cu (the Python-free hardware probe of the scan kernels) against the in-tree library."""
+    build()
+    deps = [PROBE_SRC, LIB, os.path.join(os.path.dirname(HERE), "include", "caduceus_b200.h")]
+    if not force and os.path.exists(PROBE_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(PROBE_BIN) for d in deps):
+        return PROBE_BIN
+    os.makedirs(os.path.dirname(PROBE_BIN), exist_ok=True)
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-I", os.path.join(os.path.dirname(HERE), "include"), PROBE_SRC, "-o", PROBE_BIN,
+           "-L", CSRC, "-lcaduceus_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../caduceus_b200/csrc"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {PROBE_SRC}:\n{r.stdout}")
+    return PROBE_BIN
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
+    if "--probe" in sys.argv:
+        print(build_probe(force="--force" in sys.argv))
