@@ -15,27 +15,29 @@ namespace cad {
 
 template <typename T, int N, bool REV>
 __device__ __forceinline__ void fixup_job(const cad_scan_fixup_args& a, const CUtensorMap* tmap, int job, int seq,
-                                          int pset, float* tile, float* h0_s, float* a2_s, uint64_t* bar) {
+                                          int pset, int64_t t_off, int64_t L, const float* __restrict__ h0_base,
+                                          float* tile, float* h0_s, float* a2_s, uint64_t* bar) {
+  // (t_off, L): the token range [t_off, t_off + L) this call works on — the whole sequence (0, a.L), or one in-GPU segment
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int G = blockDim.x >> 5;
-  const int64_t L = a.L, E = a.E;
+  const int64_t E = a.E;
   const int64_t ch = (int64_t)blockIdx.x * G + warp;
   const bool active = ch < E;
   const int64_t chc = active ? ch : E - 1;
   const int64_t nchunks = (L + kChunk - 1) / kChunk;
   auto phys = [](int i) { return REV ? kTok - 1 - i : i; };
 
-  const T* __restrict__ zrow = static_cast<const T*>(a.xz) + ((int64_t)seq * 2 * E + E + chc) * a.ldxz;
-  const T* __restrict__ drow = static_cast<const T*>(a.delta) + ((int64_t)job * E + chc) * a.ldd;
-  T* __restrict__ orow = static_cast<T*>(a.out) + ((int64_t)job * E + chc) * a.ldo;
+  const T* __restrict__ zrow = static_cast<const T*>(a.xz) + ((int64_t)seq * 2 * E + E + chc) * a.ldxz + t_off;
+  const T* __restrict__ drow = static_cast<const T*>(a.delta) + ((int64_t)job * E + chc) * a.ldd + t_off;
+  T* __restrict__ orow = static_cast<T*>(a.out) + ((int64_t)job * E + chc) * a.ldo + t_off;
   const int64_t pc = (int64_t)pset * E + chc;
   const float dtb = a.dt_b[pc];
   float* my_h0 = h0_s + warp * N;
   float* my_a2 = a2_s + warp * N;
   if (lane < N) {
     my_a2[lane] = a.A2[pc * N + lane];
-    my_h0[lane] = active ? a.h0[((int64_t)job * E + chc) * N + lane] : 0.f;
+    my_h0[lane] = active ? h0_base[chc * N + lane] : 0.f;
   }
   __syncwarp();
   // states still contributing (warp-uniform bit mask); a zero carry never contributes
@@ -48,6 +50,7 @@ __device__ __forceinline__ void fixup_job(const cad_scan_fixup_args& a, const CU
   tile_piece_offsets(seg, poff);
   const int c_row = job * 2 * N + N;                   // the C rows of this job
   const int blocks_per_chunk = kChunk / kBlkTok;
+  const int blk_off = (int)(t_off / kBlkTok);               // t_off is a multiple of 256
   float cum_base = 0.f;
   uint32_t parity = 0;
 
@@ -57,7 +60,7 @@ __device__ __forceinline__ void fixup_job(const cad_scan_fixup_args& a, const CU
   if (threadIdx.x == 0) {
     const int64_t first = REV ? nchunks - 1 : 0;
     mbar_expect_tx(bar, N * kChunk * 4);
-    tma_load_3d(tile, tmap, 0, (int)(first * blocks_per_chunk), c_row, bar);
+    tma_load_3d(tile, tmap, 0, blk_off + (int)(first * blocks_per_chunk), c_row, bar);
   }
 
   for (int64_t c = 0; c < nchunks; ++c) {
@@ -138,7 +141,7 @@ __device__ __forceinline__ void fixup_job(const cad_scan_fixup_args& a, const CU
     if (c + 1 < nchunks && threadIdx.x == 0) {
       const int64_t npc = REV ? pcidx - 1 : pcidx + 1;
       mbar_expect_tx(bar, N * kChunk * 4);
-      tma_load_3d(tile, tmap, 0, (int)(npc * blocks_per_chunk), c_row, bar);
+      tma_load_3d(tile, tmap, 0, blk_off + (int)(npc * blocks_per_chunk), c_row, bar);
     }
   }
 }
@@ -153,10 +156,27 @@ scan_fixup_kernel(const cad_scan_fixup_args a, const __grid_constant__ CUtensorM
   float* a2_s = h0_s + kMaxG * N;
   uint64_t* bar = reinterpret_cast<uint64_t*>(a2_s + kMaxG * N);
   if (threadIdx.x == 0) mbar_init(bar, 1);
-  const int job = blockIdx.y;
+  int job = blockIdx.y;
+  int64_t t_off = 0, L = a.L;
+  const float* h0_base;
+  if (a.nseg > 1) {
+    // blockIdx.y = (job, logical segment s >= 1); the segment's tokens = physical block k of the split used by scan variant 20
+    // (scan_fwd_v20.cuh::block_range: whole 256-token chunks, ceil(nchunks / nseg) per block)
+    const int sl = 1 + (int)(blockIdx.y % (a.nseg - 1));
+    job = (int)(blockIdx.y / (a.nseg - 1));
+    const int64_t k = a.rev_of_job[job] ? a.nseg - 1 - sl : sl;
+    const int64_t nch = (a.L + 255) / 256, per = (nch + a.nseg - 1) / a.nseg;
+    int64_t lo = k * per * 256, hi = (k + 1) * per * 256;
+    if (hi > a.L) hi = a.L;
+    if (lo >= hi) return;                                    // empty block (CTA-uniform)
+    t_off = lo; L = hi - lo;
+    h0_base = a.seg_carry + ((int64_t)job * a.nseg + sl) * a.E * N;
+  } else {
+    h0_base = a.h0 + (int64_t)job * a.E * N;
+  }
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
-  if (rev) fixup_job<T, N, true>(a, &tmap, job, seq, pset, tile, h0_s, a2_s, bar);
-  else     fixup_job<T, N, false>(a, &tmap, job, seq, pset, tile, h0_s, a2_s, bar);
+  if (rev) fixup_job<T, N, true>(a, &tmap, job, seq, pset, t_off, L, h0_base, tile, h0_s, a2_s, bar);
+  else     fixup_job<T, N, false>(a, &tmap, job, seq, pset, t_off, L, h0_base, tile, h0_s, a2_s, bar);
 }
 
 template <typename T, int N>
@@ -167,7 +187,7 @@ static int launch_fixup(const cad_scan_fixup_args& a, int G, cudaStream_t stream
   auto kern = scan_fixup_kernel<T, N>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
+  dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)(a.nseg > 1 ? a.njobs * (a.nseg - 1) : a.njobs));
   kern<<<grid, G * 32, smem, stream>>>(a, tmap);
   CAD_LAUNCH_CHECK();
   return 0;
@@ -180,8 +200,9 @@ extern "C" int cad_bimamba_scan_fixup(const cad_scan_fixup_args* a, void* stream
   CAD_REQUIRE(a, "cad_bimamba_scan_fixup: null argument block");
   CAD_REQUIRE(a->L >= 0 && a->E > 0 && a->njobs > 0 && a->nseq > 0, "cad_bimamba_scan_fixup: bad sizes");
   if (a->L == 0) return 0;
-  CAD_REQUIRE(a->xz && a->delta && a->bc && a->out && a->dt_b && a->A2 && a->h0 && a->seq_of_job && a->pset_of_job &&
-              a->rev_of_job, "cad_bimamba_scan_fixup: null pointer");
+  CAD_REQUIRE(a->xz && a->delta && a->bc && a->out && a->dt_b && a->A2 && a->seq_of_job && a->pset_of_job &&
+              a->rev_of_job && (a->nseg > 1 ? a->seg_carry != nullptr : a->h0 != nullptr), "cad_bimamba_scan_fixup: null pointer");
+  CAD_REQUIRE(a->nseg >= 0 && a->nseg <= 4096, "cad_bimamba_scan_fixup: nseg out of range");
   CAD_REQUIRE(a->N == 16, "cad_bimamba_scan_fixup: d_state = %lld not built (only 16)", (long long)a->N);
   CAD_REQUIRE(a->ldxz % 16 == 0 && a->ldd % 16 == 0 && a->ldo % 16 == 0 && a->ldbc % 32 == 0,
               "cad_bimamba_scan_fixup: bad row pitches");

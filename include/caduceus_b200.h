@@ -158,9 +158,24 @@ typedef struct {
   int32_t delta_is_dt;      /* variants 9..12, 16-bit I/O, inference only: `delta` holds dt = softplus(dt_raw + dt_b)
                                itself as FP16 (whatever io_dtype is), written by cad_conv_xproj_fwd with dt_b set: the
                                scan's prologue then has no softplus (2 of its MUFU ops per token and channel) */
+  /* variant 20 only (lane = channel; 16-bit I/O, inference: none of halo / h0 / hlast / dtsum / chunk_state / state_only): */
+  const float* bcT;         /* (njobs, ceil256(L), 2N) fp32: the B / C rows TOKEN-major, zeros beyond L (cad_bc_transpose) */
+  int32_t nseg;             /* time segments per job (grid.z), whole 256-token chunks each; 0 = 1.  Every segment is scanned
+                               from a ZERO state: with nseg > 1 `out` still lacks the carries (cad_seg_carry + cad_bimamba_scan_fixup) */
+  float* seg_state;         /* (njobs, nseg, E, N) end state of every LOGICAL segment scanned from zero; required when nseg > 1 */
+  float* seg_dtsum;         /* (njobs, nseg, E) sum of dt over the segment */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
+
+/* helpers of scan variant 20 (a sequence cut into nseg segments INSIDE one GPU; same algebra as the multi-GPU path):
+ *   cad_bc_transpose: bc (njobs, 2N, ldbc) fp32 -> bcT (njobs, ceil256(L), 2N), zeros in rows [L, ceil256(L)).
+ *   cad_seg_carry:    carry[j, s] = state entering logical segment s of job j:
+ *                       carry[j, 0] = 0,  carry[j, s+1] = exp2(A2 * seg_dtsum[j, s]) * carry[j, s] + seg_state[j, s]   (N == 16)
+ *   the carries are then applied by cad_bimamba_scan_fixup with nseg / seg_carry set.                                      */
+int cad_bc_transpose(const float* bc, float* bcT, int64_t njobs, int64_t N2, int64_t L, int64_t ldbc, void* stream);
+int cad_seg_carry(const float* seg_state, const float* seg_dtsum, const float* A2, const int32_t* pset_of_job, float* carry,
+                  int64_t njobs, int64_t nseg, int64_t E, void* stream);
 
 /* ---- carry fix-up of a sequence-sharded scan: adds, in place, the contribution of the carry-in
  *      state h0 to an output that was produced by cad_bimamba_scan_fwd with a ZERO carry:
@@ -175,6 +190,10 @@ typedef struct {
   int64_t ldxz, ldd, ldbc, ldo;
   int32_t nseq, njobs, io_dtype, channels_per_cta;
   float   cutoff_log2;      /* e.g. -40: terms below 2^-40 * |C h0| are dropped */
+  /* in-GPU segments (scan variant 20), optional: with nseg > 1 the kernel runs once per (job, logical segment s >= 1) on the
+   * segment's own token range (the split of cad_scan_fwd_args.nseg) with the carry  seg_carry[job, s]; h0 is ignored.      */
+  int32_t nseg;
+  const float* seg_carry;   /* (njobs, nseg, E, N) from cad_seg_carry */
 } cad_scan_fixup_args;
 int cad_bimamba_scan_fixup(const cad_scan_fixup_args* a, void* stream);
 

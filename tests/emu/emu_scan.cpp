@@ -9,13 +9,14 @@
 #include "../../caduceus_b200/csrc/scan_fwd_v4.cuh"
 #include "../../caduceus_b200/csrc/scan_fwd_v9.cuh"
 #include "../../caduceus_b200/csrc/scan_bwd_v2.cuh"
+#include "../../caduceus_b200/csrc/scan_fwd_v20.cuh"
 
 namespace cad {
 thread_local EmuThread g_t;
 }
 
 template <typename Body>
-static void run_cta(size_t smem_bytes, int G, int bx, int by, Body body) {
+static void run_cta(size_t smem_bytes, int G, int bx, int by, Body body, int bz = 0) {
   using namespace cad;
   EmuCta cta;
   cta.smem_bytes = smem_bytes;
@@ -31,7 +32,7 @@ static void run_cta(size_t smem_bytes, int G, int bx, int by, Body body) {
   std::vector<std::thread> th;
   for (int t = 0; t < cta.nthreads; ++t)
     th.emplace_back([&, t] {
-      g_t = EmuThread{&cta, t, bx, by};
+      g_t = EmuThread{&cta, t, bx, by, bz};
       body(cta.smem);
     });
   for (auto& t : th) t.join();
@@ -124,5 +125,22 @@ extern "C" int emu_scan_bwd_v2(const cad_scan_bwd_args* a, int G) {
       else if (a->io_dtype == CAD_F16) run_cta(sb, G, bx, by, [&](unsigned char* sm) { bw2::kernel_body<__half>(*a, &tmap, sm); });
       else run_cta(sb, G, bx, by, [&](unsigned char* sm) { bw2::kernel_body<float>(*a, &tmap, sm); });
     }
+  return 0;
+}
+
+// variant 20 (lane = channel): W warps of 32 channels per CTA, grid (channel groups, jobs, segments)
+extern "C" int emu_scan_v20(const cad_scan_fwd_args* a, int W) {
+  using namespace cad;
+  if (a->N != v20::NST || W < 1 || W > v20::kMaxW || a->io_dtype == CAD_F32 || !a->bcT) return -1;
+  if (a->L <= 0) return 0;
+  const int nseg = a->nseg > 0 ? a->nseg : 1;
+  const int gx = (int)(((a->E + 31) / 32 + W - 1) / W);
+  const size_t sb = v20::smem_bytes(W);
+  for (int bz = 0; bz < nseg; ++bz)
+    for (int by = 0; by < a->njobs; ++by)
+      for (int bx = 0; bx < gx; ++bx) {
+        if (a->io_dtype == CAD_BF16) run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<__nv_bfloat16>(*a, sm); }, bz);
+        else run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<__half>(*a, sm); }, bz);
+      }
   return 0;
 }

@@ -69,7 +69,7 @@ struct EmuCta {
   bool deadlock = false;
 };
 
-struct EmuThread { EmuCta* cta; int tid, bx, by; };
+struct EmuThread { EmuCta* cta; int tid, bx, by, bz = 0; };
 extern thread_local EmuThread g_t;
 
 namespace v4 {
@@ -226,6 +226,24 @@ inline void scan_step1(float& P, float& H, int lane) {
 }
 inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 }  // namespace v9
+
+namespace v20 {
+#define CAD_BIDZ (::cad::g_t.bz)
+// 1-D bulk copy: synchronous here; alignment and bounds as the TMA engine wants them
+inline void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  if ((smem_dst & 15) || ((uintptr_t)gsrc & 15) || (bytes & 15)) { fprintf(stderr, "emu: misaligned bulk copy\n"); abort(); }
+  memcpy(smem_at(smem_dst, bytes), gsrc, bytes);
+  std::lock_guard<std::mutex> g(g_t.cta->m);
+  Mbar& mb = g_t.cta->mbars.at(bar);
+  mb.tx -= (long)bytes;
+  mbar_complete_locked(mb);
+}
+template <int N> inline void cp_wait_group() {}        // cp.async is an immediate copy here
+inline void stg128f(float* p, float a, float b, float c, float d) {
+  if ((uintptr_t)p & 15) { fprintf(stderr, "emu: misaligned 16-byte global store\n"); abort(); }
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+}
+}  // namespace v20
 
 namespace bw2 {
 inline float shfl_down1(float v, int off) { const int l = g_t.tid & 31; return v4::shfl_raw(v, l + off < 32 ? l + off : l); }
