@@ -16,6 +16,7 @@ _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
 SCAN_TOKENS_PER_LANE = 0   # 0 = library default; 8 / 16 force the scan's tokens per lane (tuning knob)
 SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7 / 9..12: see cad_scan_fwd_args.variant
+SCAN_NSEG = int(__import__("os").environ.get("CAD_SCAN_NSEG", "0"))   # variant 20: time segments per job (0 = pick from the grid)
 SCAN_DT_IN_XPROJ = __import__("os").environ.get("CAD_DT_IN_XPROJ", "0") == "1"   # variants 9..12: dt = softplus(.) leaves conv_xproj as fp16
 SCAN_BWD_VARIANT = int(__import__("os").environ.get("CAD_SCAN_BWD_VARIANT", "0"))   # 0 = library default; 1 / 2: see cad_scan_bwd_args.variant
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
@@ -293,9 +294,11 @@ def project_dt_bc(xdbl, dt_w_job, L, N):
 
 
 def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
-             channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None, bc16=None, delta_is_dt=False):
+             channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None, bc16=None, delta_is_dt=False,
+             nseg=None):
     """Launch the fused bidirectional scan.
-    xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld)."""
+    xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld).
+    nseg: time segments per job for variant 20 (None = SCAN_NSEG / a grid of about two CTAs per SM)."""
     lib = _lib.load()
     seq, pset, rev = jobs
     conv_w4, conv_b, dt_b, A2, Dk = packed
@@ -318,6 +321,10 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
         L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only),
         SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0, None, 0, int(delta_is_dt))
     a.variant = scan_variant(a) if variant is None else int(variant)
+    if a.variant == 20:
+        if halo is not None or h0 is not None or want_state or want_chunk_state or state_only:
+            raise RuntimeError("scan variant 20 covers inference only (no halo / h0 / states)")
+        return scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=nseg, warps_per_cta=channels_per_cta), None, None, None
     if a.variant in (9, 10):
         # 16-bit copy of the B / C rows for the 16-bit-tile kernels (experimental path: a cast per call until the
         # conv_xproj kernel writes it directly); columns [L, ldbc16) must be zero
@@ -337,6 +344,57 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     return out, hlast, dtsum, cstate
 
 
+def default_nseg(njobs, E, L, warps_per_cta=8):
+    """Segments per job for scan variant 20: enough (job, segment, channel-group) CTAs for two per SM, segments of whole
+    256-token chunks and never shorter than 2048 tokens (each segment boundary costs a carry fix-up)."""
+    if SCAN_NSEG > 0:
+        return SCAN_NSEG
+    sms = _lib.load().cad_sm_count() or 148
+    groups = -(-((E + 31) // 32) // max(1, warps_per_cta))
+    want = max(1, (2 * sms) // max(1, njobs * groups))
+    return max(1, min(want, L // 2048))
+
+
+def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-40.0):
+    """Scan variant 20 (lane = channel, csrc/scan_fwd_v20.cuh): token-major copy of B / C, every segment scanned from a zero
+    state, carries composed (cad_seg_carry) and added in place by the segment mode of the fix-up kernel.  `a` is the
+    marshalled argument block of scan_fwd (reused so that the two paths cannot drift apart)."""
+    lib = _lib.load()
+    seq, pset, rev = jobs
+    conv_w4, conv_b, dt_b, A2, Dk = packed
+    njobs, twoN, ldbc = bc.shape
+    E, N, dev = a.E, twoN // 2, xz.device
+    W = warps_per_cta if warps_per_cta > 0 else min(8, (E + 31) // 32)
+    nseg = default_nseg(njobs, E, L, W) if nseg is None else int(nseg)
+    Lp = round_up(max(L, 1), 256)
+    bcT = torch.empty(njobs, Lp, twoN, device=dev, dtype=torch.float32)
+    _lib.check(lib.cad_bc_transpose(_ptr(bc), _ptr(bcT), njobs, twoN, L, ldbc, _stream()), "cad_bc_transpose")
+    seg_state = torch.empty(njobs, nseg, E, N, device=dev, dtype=torch.float32)
+    seg_dtsum = torch.empty(njobs, nseg, E, device=dev, dtype=torch.float32)
+    a.bcT, a.nseg, a.seg_state, a.seg_dtsum, a.channels_per_cta = _ptr(bcT), nseg, _ptr(seg_state), _ptr(seg_dtsum), W
+    ev = None
+    if SCAN_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.check(lib.cad_bimamba_scan_fwd(C.byref(a), _stream()), "cad_bimamba_scan_fwd")
+    _launched(2)
+    if nseg > 1:
+        carry = torch.empty(njobs, nseg, E, N, device=dev, dtype=torch.float32)
+        _lib.check(lib.cad_seg_carry(_ptr(seg_state), _ptr(seg_dtsum), _ptr(A2), _ptr(pset), _ptr(carry), njobs, nseg, E,
+                                     _stream()), "cad_seg_carry")
+        if a.delta_is_dt:
+            raise RuntimeError("scan variant 20 with nseg > 1 needs dt_raw (the fix-up kernel applies the softplus itself)")
+        f = _lib.ScanFixupArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
+                               _ptr(rev), None, L, E, N, a.ldxz, a.ldd, ldbc, a.ldo, a.nseq, njobs, a.io_dtype, 0,
+                               float(cutoff_log2), nseg, _ptr(carry))
+        _lib.check(lib.cad_bimamba_scan_fixup(C.byref(f), _stream()), "cad_bimamba_scan_fixup")
+        _launched(2)
+    if ev is not None:
+        ev[1].record()
+        SCAN_EVENTS.append(ev)
+    return out
+
+
 def scan_variant(a):
     """Kernel variant for a forward-scan call when the caller did not force one: SCAN_VARIANT (env CAD_SCAN_VARIANT)
     where that variant covers the call (variant 4 is inference-only), else the library default."""
@@ -346,6 +404,10 @@ def scan_variant(a):
         return 4 if ok else 0
     if SCAN_VARIANT in (9, 10, 11, 12):
         return SCAN_VARIANT if (a.io_dtype != CAD_F32 and a.N == 16 and a.tokens_per_lane in (0, 16)) else 0
+    if SCAN_VARIANT == 20:
+        ok = (a.io_dtype != CAD_F32 and a.N == 16 and not (a.halo or a.h0 or a.hlast or a.dtsum or a.chunk_state)
+              and not a.state_only)
+        return 20 if ok else 0
     return SCAN_VARIANT
 
 

@@ -5,6 +5,7 @@
 //     and its launch time (CUDA events, min / mean of 5 after 2 warm-ups); variants 10 / 12 also with dt precomputed
 //   group B (backward, Caduceus-Ph shape: 2 jobs): variant 2 against variant 1 on every gradient, and both times.
 //   group C (conv_xproj): the optional bc16 / dt outputs against the plain outputs of the same kernel, and both times.
+//   group D (scan variant 20, lane = channel): the whole in-GPU segment pipeline against variant 3, stage by stage.
 // Each group runs in its own process (fork before any CUDA call) so that a trap in one kernel cannot take the other
 // group's results with it; every line is flushed to gpurun_out/hw_probe.log as soon as it is known.
 //
@@ -326,10 +327,64 @@ static int group_xproj(int64_t L) {
   return 0;
 }
 
+// group D: scan variant 20 (lane = channel, in-GPU time segments): pass A alone with one segment (exactly the default
+// kernel's semantics), then the full pipeline (transpose, zero-carry segment scans, carry composition, segment fix-up)
+// for several (segments, warps per CTA) against variant 3, with the time of every stage
+static int group_v20(int64_t L) {
+  CK(cudaFree(0));
+  Problem p;
+  if (make_problem(p, L, 4)) return 1;
+  const int64_t E = p.E, N = p.N, n_out = (int64_t)p.njobs * E * L, Lp = (L + 255) / 256 * 256;
+  cad_scan_fwd_args r = fwd_args(p, 3, false, p.out_ref);
+  if (cad_bimamba_scan_fwd(&r, nullptr)) { say("D: v3 reference failed: %s", cad_last_error()); return 1; }
+  float *bcT, *seg_state, *seg_dtsum, *carry;
+  const int max_seg = 64;
+  CK(cudaMalloc(&bcT, (size_t)p.njobs * Lp * 2 * N * 4));
+  CK(cudaMalloc(&seg_state, (size_t)p.njobs * max_seg * E * N * 4));
+  CK(cudaMalloc(&carry, (size_t)p.njobs * max_seg * E * N * 4));
+  CK(cudaMalloc(&seg_dtsum, (size_t)p.njobs * max_seg * E * 4));
+  float tmin, tmean;
+  if (time_launches([&]() { return cad_bc_transpose(p.bc, bcT, p.njobs, 2 * N, L, L, nullptr); }, 1, 4, &tmin, &tmean)) return 1;
+  say("D: cad_bc_transpose (64 MiB in, 64 MiB out)  min %.3f ms mean %.3f ms", tmin, tmean);
+  struct Cfg { int nseg, W; };
+  const Cfg cfgs[] = {{1, 8}, {37, 8}, {18, 8}, {9, 8}, {37, 4}, {74, 4}, {18, 4}, {64, 8}};
+  for (const Cfg& c : cfgs) {
+    cad_scan_fwd_args a = fwd_args(p, 20, false, p.out_var);
+    a.bc = nullptr; a.bcT = bcT; a.nseg = c.nseg; a.seg_state = seg_state; a.seg_dtsum = seg_dtsum; a.channels_per_cta = c.W;
+    cad_scan_fixup_args f;
+    memset(&f, 0, sizeof f);
+    f.xz = p.xz; f.delta = p.delta; f.bc = p.bc; f.out = p.out_var; f.dt_b = p.dt_b; f.A2 = p.A2;
+    f.seq_of_job = p.seq; f.pset_of_job = p.pset; f.rev_of_job = p.rev;
+    f.L = L; f.E = E; f.N = N; f.ldxz = L; f.ldd = L; f.ldbc = L; f.ldo = L;
+    f.nseq = p.nseq; f.njobs = p.njobs; f.io_dtype = CAD_BF16; f.cutoff_log2 = -40.f; f.nseg = c.nseg; f.seg_carry = carry;
+    auto pass_a = [&]() { int rc = cad_bimamba_scan_fwd(&a, nullptr); if (rc) say("D: v20 launch rc %d: %s", rc, cad_last_error()); return rc; };
+    auto compose = [&]() { return c.nseg > 1 ? cad_seg_carry(seg_state, seg_dtsum, p.A2, p.pset, carry, p.njobs, c.nseg, E, nullptr) : 0; };
+    auto fixup = [&]() { int rc = c.nseg > 1 ? cad_bimamba_scan_fixup(&f, nullptr) : 0; if (rc) say("D: fix-up rc %d: %s", rc, cad_last_error()); return rc; };
+    CK(cudaMemset(p.out_var, 0xFF, (size_t)n_out * 2));
+    if (pass_a() || compose() || fixup()) return 1;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { say("D: v20 nseg %d W %d FAILED at run time: %s", c.nseg, c.W, cudaGetErrorString(e)); return 1; }
+    Cmp m;
+    if (cmp<__nv_bfloat16>(p.out_var, p.out_ref, n_out, p.stats, &m)) return 1;
+    float ta, tam, tc = 0.f, tcm = 0.f, tf = 0.f, tfm = 0.f, tall, tallm;
+    const int it = c.nseg == 1 ? 2 : 5;
+    if (time_launches(pass_a, 1, it, &ta, &tam)) return 1;
+    if (c.nseg > 1) {
+      if (time_launches(compose, 1, it, &tc, &tcm)) return 1;
+      // the fix-up adds in place: time it on its own (the values drift, the work does not)
+      if (time_launches(fixup, 1, it, &tf, &tfm)) return 1;
+    }
+    if (time_launches([&]() { return pass_a() || compose() || fixup(); }, 1, it, &tall, &tallm)) return 1;
+    say("D: v20 nseg %2d W %d  max|diff vs v3| %.3e (max|ref| %.3e, non-finite %u)   pass A %.3f  carry %.3f  fix-up %.3f  "
+        "whole pipeline min %.3f mean %.3f ms", c.nseg, c.W, m.maxdiff, m.maxref, m.bad, ta, tc, tf, tall, tallm);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   g_t0 = now_s();
   const int64_t L = argc > 1 ? atoll(argv[1]) : 131072;
-  const char* only = argc > 2 ? argv[2] : "ABC";
+  const char* only = argc > 2 ? argv[2] : "ABCD";
   if (system("mkdir -p gpurun_out") != 0) return 2;
   g_log = fopen("gpurun_out/hw_probe.log", "a");
   say("hw_probe: L = %lld, groups %s", (long long)L, only);
@@ -337,7 +392,7 @@ int main(int argc, char** argv) {
   for (const char* g = only; *g; ++g) {
     fflush(stdout); if (g_log) fflush(g_log);
     const pid_t pid = fork();                       // before any CUDA call in this process
-    if (pid == 0) { const int r = (*g == 'A') ? group_forward(L) : (*g == 'B') ? group_backward(L) : group_xproj(L); fflush(stdout); _exit(r); }
+    if (pid == 0) { const int r = (*g == 'A') ? group_forward(L) : (*g == 'B') ? group_backward(L) : (*g == 'C') ? group_xproj(L) : group_v20(L); fflush(stdout); _exit(r); }
     int st = 0;
     waitpid(pid, &st, 0);
     say("group %c finished: %s %d", *g, WIFEXITED(st) ? "exit" : "signal", WIFEXITED(st) ? WEXITSTATUS(st) : WTERMSIG(st));

@@ -17,13 +17,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _run(L, E, spec, dtype, G, seed, variant):
+def _run(L, E, spec, dtype, G, seed, variant, **kw):
     from caduceus_b200 import functional as CF
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, seed)
     bc = bc.to(dtype).float()      # values every variant (fp32 or 16-bit tile) represents exactly
     d = lambda t: t.to(DEV).contiguous()   # noqa: E731
     out, _, _, _ = CF.scan_fwd(d(xz), d(delta), d(bc), tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)),
-                               tuple(d(t) for t in tabs), L, channels_per_cta=G, variant=variant)
+                               tuple(d(t) for t in tabs), L, channels_per_cta=G, variant=variant, **kw)
     torch.cuda.synchronize()
     f = lambda t: t.float().numpy()   # noqa: E731
     ref = boundary_ref(f(xz), f(delta), f(bc), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk),
@@ -137,6 +137,42 @@ def test_v9_to_v12_hooks_vs_boundary_restatement(rev, variant):
         assert np.allclose(got, r, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(r).max())), (name, np.abs(got - r).max())
 
 
+@unmeasured
+@pytest.mark.parametrize("nseg", [1, 3, 7])
+@pytest.mark.parametrize("L", [1, 257, 2300, 9000])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_v20_lane_per_channel_vs_boundary_restatement(L, rev, nseg):
+    """variant 20 end to end (token-major B / C copy, zero-carry segment scans, carry composition, segment fix-up) on the
+    same checker; nseg = 7 leaves empty blocks at the short lengths."""
+    got, ref = _run(L, 96, [(0, 0, rev), (0, 1, 1 - rev)], torch.bfloat16, 0, 600 + L, 20, nseg=nseg)
+    # two roundings to bf16 where a carry term is added to an already rounded partial result
+    err, bound = np.abs(got - ref), 1e-2 + 1.5e-2 * np.abs(ref)
+    assert np.isfinite(got).all() and (err <= bound).all(), (err.max(), (err - bound).max())
+
+
+@unmeasured
+def test_v20_helpers_transpose_and_carry_composition():
+    from caduceus_b200 import _lib, functional as CF
+    import ctypes as C
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    njobs, L, E, nseg = 3, 700, 40, 5
+    bc = torch.randn(njobs, 32, 704, generator=g).to(DEV)
+    bcT = torch.full((njobs, 768, 32), float("nan"), device=DEV)
+    p = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+    _lib.check(lib.cad_bc_transpose(p(bc), p(bcT), njobs, 32, L, 704, CF._stream()), "cad_bc_transpose")
+    assert torch.equal(bcT[:, :L], bc[..., :L].transpose(1, 2)) and (bcT[:, L:] == 0).all()
+    st, ds = torch.randn(njobs, nseg, E, 16, generator=g).to(DEV), torch.rand(njobs, nseg, E, generator=g).to(DEV)
+    A2 = -(torch.rand(2, E, 16, generator=g) * 8).to(DEV)
+    pset = torch.tensor([0, 1, 0], dtype=torch.int32, device=DEV)
+    carry = torch.empty(njobs, nseg, E, 16, device=DEV)
+    _lib.check(lib.cad_seg_carry(p(st), p(ds), p(A2), p(pset), p(carry), njobs, nseg, E, CF._stream()), "cad_seg_carry")
+    h = torch.zeros(njobs, E, 16, device=DEV, dtype=torch.float64)
+    for s_ in range(nseg):
+        assert torch.allclose(carry[:, s_].double(), h, rtol=1e-4, atol=1e-5), s_
+        h = torch.exp2(A2[pset.long()].double() * ds[:, s_, :, None].double()) * h + st[:, s_].double()
+
+
 def test_v4_rejects_what_it_does_not_cover():
     from caduceus_b200 import functional as CF
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(100, 8, [(0, 0, 0)], torch.float32, 0)
@@ -173,7 +209,7 @@ def test_conv_xproj_dt_epilogue_matches_softplus_of_its_own_dt_raw(dtype):
 
 @pytest.mark.parametrize("variant", [4, pytest.param(9, marks=unmeasured), pytest.param(10, marks=unmeasured),
                                      pytest.param(12, marks=unmeasured), pytest.param(-10, marks=unmeasured),
-                                     pytest.param(-12, marks=unmeasured)])
+                                     pytest.param(-12, marks=unmeasured), pytest.param(20, marks=unmeasured)])
 @pytest.mark.parametrize("tag", ["ps_small", "ph_config0"])
 def test_model_forward_with_scan_variant_vs_reference_fixture(tag, variant):
     """The whole model with the scan forced to a non-default variant (9 / 10 take their 16-bit tile straight from the
