@@ -515,7 +515,7 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   CAD_REQUIRE(a, "cad_bimamba_scan_fwd: null argument block");
   CAD_REQUIRE(a->L >= 0 && a->E > 0 && a->njobs > 0 && a->nseq > 0, "cad_bimamba_scan_fwd: bad sizes");
   if (a->L == 0) return 0;
-  CAD_REQUIRE(a->xz && a->delta && (a->bc || a->variant == 9 || a->variant == 10 || a->variant == 20) && (a->out || a->state_only) && a->conv_w && a->conv_b && a->dt_b && a->A2 && a->Dskip &&
+  CAD_REQUIRE(a->xz && a->delta && (a->bc || a->variant == 9 || a->variant == 10 || a->variant >= 20) && (a->out || a->state_only) && a->conv_w && a->conv_b && a->dt_b && a->A2 && a->Dskip &&
               a->seq_of_job && a->pset_of_job && a->rev_of_job, "cad_bimamba_scan_fwd: null pointer");
   CAD_REQUIRE(a->N == 16, "cad_bimamba_scan_fwd: d_state = %lld not built (only 16)", (long long)a->N);
   CAD_REQUIRE(a->K >= 1 && a->K <= 4, "cad_bimamba_scan_fwd: d_conv = %lld out of range [1, 4]", (long long)a->K);
@@ -527,10 +527,10 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4 || a->variant == 7 || (a->variant >= 9 && a->variant <= 12) ||
-              a->variant == 20, "cad_bimamba_scan_fwd: variant must be 0, 3, 4, 7, 9..12 or 20");
+              (a->variant >= 20 && a->variant <= 23), "cad_bimamba_scan_fwd: variant must be 0, 3, 4, 7, 9..12 or 20..23");
   CAD_REQUIRE(!a->delta_is_dt || (a->variant >= 9 && a->io_dtype != CAD_F32 && !a->chunk_state),
               "cad_bimamba_scan_fwd: delta_is_dt needs variant 9..12 or 20, 16-bit I/O and no saved chunk states (inference)");
-  if (a->variant == 20) return launch_scan_v20(*a, stream);
+  if (a->variant >= 20) return launch_scan_v20(*a, stream);
   if (a->variant == 4) {
     CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
                 "halo / h0 / hlast / dtsum / chunk_state / state_only");

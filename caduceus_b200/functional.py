@@ -321,7 +321,7 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
         L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only),
         SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0, None, 0, int(delta_is_dt))
     a.variant = scan_variant(a) if variant is None else int(variant)
-    if a.variant == 20:
+    if a.variant in (20, 21, 22, 23):
         if halo is not None or h0 is not None or want_state or want_chunk_state or state_only:
             raise RuntimeError("scan variant 20 covers inference only (no halo / h0 / states)")
         return scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=nseg, warps_per_cta=channels_per_cta), None, None, None
@@ -404,10 +404,10 @@ def scan_variant(a):
         return 4 if ok else 0
     if SCAN_VARIANT in (9, 10, 11, 12):
         return SCAN_VARIANT if (a.io_dtype != CAD_F32 and a.N == 16 and a.tokens_per_lane in (0, 16)) else 0
-    if SCAN_VARIANT == 20:
+    if SCAN_VARIANT in (20, 21, 22, 23):
         ok = (a.io_dtype != CAD_F32 and a.N == 16 and not (a.halo or a.h0 or a.hlast or a.dtsum or a.chunk_state)
               and not a.state_only)
-        return 20 if ok else 0
+        return SCAN_VARIANT if ok else 0
     return SCAN_VARIANT
 
 

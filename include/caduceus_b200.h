@@ -158,7 +158,10 @@ typedef struct {
   int32_t delta_is_dt;      /* variants 9..12, 16-bit I/O, inference only: `delta` holds dt = softplus(dt_raw + dt_b)
                                itself as FP16 (whatever io_dtype is), written by cad_conv_xproj_fwd with dt_b set: the
                                scan's prologue then has no softplus (2 of its MUFU ops per token and channel) */
-  /* variant 20 only (lane = channel; 16-bit I/O, inference: none of halo / h0 / hlast / dtsum / chunk_state / state_only): */
+  /* variants 20..23 only (lane = channel: a warp owns 32 channels and walks time serially, 16 states per lane as packed pairs,
+     B / C as broadcast reads, no shuffles; 21..23 take the exp2 of 1 / 2 / 3 of the 8 state pairs from a polynomial on the FMA
+     pipe instead of MUFU; channels_per_cta then counts WARPS per CTA, <= 8; 16-bit I/O, inference: none of halo / h0 / hlast /
+     dtsum / chunk_state / state_only): */
   const float* bcT;         /* (njobs, ceil256(L), 2N) fp32: the B / C rows TOKEN-major, zeros beyond L (cad_bc_transpose) */
   int32_t nseg;             /* time segments per job (grid.z), whole 256-token chunks each; 0 = 1.  Every segment is scanned
                                from a ZERO state: with nseg > 1 `out` still lacks the carries (cad_seg_carry + cad_bimamba_scan_fixup) */

@@ -346,10 +346,11 @@ static int group_v20(int64_t L) {
   float tmin, tmean;
   if (time_launches([&]() { return cad_bc_transpose(p.bc, bcT, p.njobs, 2 * N, L, L, nullptr); }, 1, 4, &tmin, &tmean)) return 1;
   say("D: cad_bc_transpose (64 MiB in, 64 MiB out)  min %.3f ms mean %.3f ms", tmin, tmean);
-  struct Cfg { int nseg, W; };
-  const Cfg cfgs[] = {{1, 8}, {37, 8}, {18, 8}, {9, 8}, {37, 4}, {74, 4}, {18, 4}, {64, 8}};
+  struct Cfg { int nseg, W, variant; };
+  const Cfg cfgs[] = {{1, 8, 20}, {37, 8, 20}, {18, 8, 20}, {9, 8, 20}, {37, 4, 20}, {74, 4, 20}, {18, 4, 20}, {64, 8, 20},
+                      {37, 8, 21}, {37, 8, 22}, {37, 8, 23}, {18, 8, 22}};      // 21..23: exp2 of 1 / 2 / 3 state pairs on the FMA pipe
   for (const Cfg& c : cfgs) {
-    cad_scan_fwd_args a = fwd_args(p, 20, false, p.out_var);
+    cad_scan_fwd_args a = fwd_args(p, c.variant, false, p.out_var);
     a.bc = nullptr; a.bcT = bcT; a.nseg = c.nseg; a.seg_state = seg_state; a.seg_dtsum = seg_dtsum; a.channels_per_cta = c.W;
     cad_scan_fixup_args f;
     memset(&f, 0, sizeof f);
@@ -375,8 +376,8 @@ static int group_v20(int64_t L) {
       if (time_launches(fixup, 1, it, &tf, &tfm)) return 1;
     }
     if (time_launches([&]() { return pass_a() || compose() || fixup(); }, 1, it, &tall, &tallm)) return 1;
-    say("D: v20 nseg %2d W %d  max|diff vs v3| %.3e (max|ref| %.3e, non-finite %u)   pass A %.3f  carry %.3f  fix-up %.3f  "
-        "whole pipeline min %.3f mean %.3f ms", c.nseg, c.W, m.maxdiff, m.maxref, m.bad, ta, tc, tf, tall, tallm);
+    say("D: v%d nseg %2d W %d  max|diff vs v3| %.3e (max|ref| %.3e, non-finite %u)   pass A %.3f  carry %.3f  fix-up %.3f  "
+        "whole pipeline min %.3f mean %.3f ms", c.variant, c.nseg, c.W, m.maxdiff, m.maxref, m.bad, ta, tc, tf, tall, tallm);
   }
   return 0;
 }

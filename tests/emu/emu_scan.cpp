@@ -129,6 +129,16 @@ extern "C" int emu_scan_bwd_v2(const cad_scan_bwd_args* a, int G) {
 }
 
 // variant 20 (lane = channel): W warps of 32 channels per CTA, grid (channel groups, jobs, segments)
+template <typename T>
+static void run_v20(const cad_scan_fwd_args* a, size_t sb, int W, int bx, int by, int bz) {
+  using namespace cad;
+  switch (a->variant - 20) {
+    case 1: run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<T, 1>(*a, sm); }, bz); break;
+    case 2: run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<T, 2>(*a, sm); }, bz); break;
+    case 3: run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<T, 3>(*a, sm); }, bz); break;
+    default: run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<T, 0>(*a, sm); }, bz); break;
+  }
+}
 extern "C" int emu_scan_v20(const cad_scan_fwd_args* a, int W) {
   using namespace cad;
   if (a->N != v20::NST || W < 1 || W > v20::kMaxW || a->io_dtype == CAD_F32 || !a->bcT) return -1;
@@ -139,8 +149,8 @@ extern "C" int emu_scan_v20(const cad_scan_fwd_args* a, int W) {
   for (int bz = 0; bz < nseg; ++bz)
     for (int by = 0; by < a->njobs; ++by)
       for (int bx = 0; bx < gx; ++bx) {
-        if (a->io_dtype == CAD_BF16) run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<__nv_bfloat16>(*a, sm); }, bz);
-        else run_cta(sb, W, bx, by, [&](unsigned char* sm) { v20::kernel_body<__half>(*a, sm); }, bz);
+        if (a->io_dtype == CAD_BF16) run_v20<__nv_bfloat16>(a, sb, W, bx, by, bz);
+        else run_v20<__half>(a, sb, W, bx, by, bz);
       }
   return 0;
 }

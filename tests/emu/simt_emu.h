@@ -239,6 +239,8 @@ inline void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, ui
   mbar_complete_locked(mb);
 }
 template <int N> inline void cp_wait_group() {}        // cp.async is an immediate copy here
+inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline void stg128f(float* p, float a, float b, float c, float d) {
   if ((uintptr_t)p & 15) { fprintf(stderr, "emu: misaligned 16-byte global store\n"); abort(); }
   p[0] = a; p[1] = b; p[2] = c; p[3] = d;
