@@ -355,10 +355,12 @@ def default_nseg(njobs, E, L, warps_per_cta=8):
     return max(1, min(want, L // 2048))
 
 
-def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-40.0):
+def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-24.0):
     """Scan variant 20 (lane = channel, csrc/scan_fwd_v20.cuh): token-major copy of B / C, every segment scanned from a zero
     state, carries composed (cad_seg_carry) and added in place by the segment mode of the fix-up kernel.  `a` is the
-    marshalled argument block of scan_fwd (reused so that the two paths cannot drift apart)."""
+    marshalled argument block of scan_fwd (reused so that the two paths cannot drift apart).  cutoff_log2: a carry term is
+    dropped once its decay factor is below 2^cutoff — 2^-24 is 4 decimal orders under the ulp of the 16-bit outputs this
+    variant is restricted to (the multi-GPU path keeps 2^-40 because it also serves fp32 I/O)."""
     lib = _lib.load()
     seq, pset, rev = jobs
     conv_w4, conv_b, dt_b, A2, Dk = packed

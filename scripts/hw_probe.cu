@@ -357,7 +357,7 @@ static int group_v20(int64_t L) {
     f.xz = p.xz; f.delta = p.delta; f.bc = p.bc; f.out = p.out_var; f.dt_b = p.dt_b; f.A2 = p.A2;
     f.seq_of_job = p.seq; f.pset_of_job = p.pset; f.rev_of_job = p.rev;
     f.L = L; f.E = E; f.N = N; f.ldxz = L; f.ldd = L; f.ldbc = L; f.ldo = L;
-    f.nseq = p.nseq; f.njobs = p.njobs; f.io_dtype = CAD_BF16; f.cutoff_log2 = -40.f; f.nseg = c.nseg; f.seg_carry = carry;
+    f.nseq = p.nseq; f.njobs = p.njobs; f.io_dtype = CAD_BF16; f.cutoff_log2 = -24.f; f.nseg = c.nseg; f.seg_carry = carry;
     auto pass_a = [&]() { int rc = cad_bimamba_scan_fwd(&a, nullptr); if (rc) say("D: v20 launch rc %d: %s", rc, cad_last_error()); return rc; };
     auto compose = [&]() { return c.nseg > 1 ? cad_seg_carry(seg_state, seg_dtsum, p.A2, p.pset, carry, p.njobs, c.nseg, E, nullptr) : 0; };
     auto fixup = [&]() { int rc = c.nseg > 1 ? cad_bimamba_scan_fixup(&f, nullptr) : 0; if (rc) say("D: fix-up rc %d: %s", rc, cad_last_error()); return rc; };
