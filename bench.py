@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--graph", action="store_true",
                     help="replay the forward from a CUDA graph (single-GPU / replica forward only; helps short sequences)")
     ap.add_argument("--scan-tok", type=int, default=0, choices=[0, 8, 16], help="tokens per lane of the scan kernel (tuning)")
-    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4, 7, 9, 10, 11, 12],
+    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4, 7, 9, 10, 11, 12, 20, 21, 22, 23],
                     help="forward-scan kernel variant (cad_scan_fwd_args.variant); default: env CAD_SCAN_VARIANT / library default")
     ap.add_argument("--shard", default="none", choices=["none", "seq"],
                     help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
@@ -353,7 +353,13 @@ def run_b200(a):
                 traffic = tj[a.model + ("_v4" if scan_v4 else "")]["dram_bytes_per_launch"]
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "bimamba_scan_fwd_v4_kernel" if scan_v4 else "bimamba_scan_fwd_kernel", "achieved": achieved, "peak": peak,
+        plain = not train and not shard_seq           # the non-default variants cover the plain inference call
+        kname = ("bimamba_scan_fwd_v4_kernel" if scan_v4 else
+                 "bimamba_scan_fwd_v9_kernel" if CF.SCAN_VARIANT in (9, 10) and plain else
+                 "bimamba_scan_fwd_v11_kernel" if CF.SCAN_VARIANT in (11, 12) and plain else
+                 "bimamba_scan_fwd_v20_kernel (+ bc_transpose, seg_carry, scan_fixup: the whole segmented scan is timed)"
+                 if CF.SCAN_VARIANT >= 20 and plain else "bimamba_scan_fwd_kernel")
+        roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "6.65 TB/s (of fallback)",

@@ -17,7 +17,7 @@ ap.add_argument("--model", default="ps", help="ps, ph or ps,ph")
 ap.add_argument("--L", type=int, default=131072)
 ap.add_argument("--E", type=int, default=512)
 ap.add_argument("--iters", type=int, default=10)
-ap.add_argument("--variants", default="3,7,9,10,11,12,4")
+ap.add_argument("--variants", default="3,7,9,10,11,12,4,20,22")
 args = ap.parse_args()
 
 dev = "cuda"
