@@ -366,7 +366,8 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     conv_w4, conv_b, dt_b, A2, Dk = packed
     njobs, twoN, ldbc = bc.shape
     E, N, dev = a.E, twoN // 2, xz.device
-    W = warps_per_cta if warps_per_cta > 0 else min(8, (E + 31) // 32)
+    # warps (32 channels each) per CTA: fewer when there are few jobs, so that about 37 segments per job fill two CTAs per SM
+    W = warps_per_cta if warps_per_cta > 0 else min(8 if njobs >= 4 else 4 if njobs >= 2 else 2, (E + 31) // 32)
     nseg = default_nseg(njobs, E, L, W) if nseg is None else int(nseg)
     Lp = round_up(max(L, 1), 256)
     bcT = torch.empty(njobs, Lp, twoN, device=dev, dtype=torch.float32)

@@ -347,7 +347,7 @@ static int group_v20(int64_t L) {
   if (time_launches([&]() { return cad_bc_transpose(p.bc, bcT, p.njobs, 2 * N, L, L, nullptr); }, 1, 4, &tmin, &tmean)) return 1;
   say("D: cad_bc_transpose (64 MiB in, 64 MiB out)  min %.3f ms mean %.3f ms", tmin, tmean);
   struct Cfg { int nseg, W, variant; };
-  const Cfg cfgs[] = {{1, 8, 20}, {37, 8, 20}, {18, 8, 20}, {9, 8, 20}, {37, 4, 20}, {74, 4, 20}, {18, 4, 20}, {64, 8, 20},
+  const Cfg cfgs[] = {{1, 8, 20}, {37, 8, 20}, {18, 8, 20}, {18, 4, 20}, {9, 4, 20}, {9, 2, 20}, {5, 2, 20}, {37, 4, 20}, {74, 4, 20},
                       {37, 8, 21}, {37, 8, 22}, {37, 8, 23}, {18, 8, 22}};      // 21..23: exp2 of 1 / 2 / 3 state pairs on the FMA pipe
   for (const Cfg& c : cfgs) {
     cad_scan_fwd_args a = fwd_args(p, c.variant, false, p.out_var);
