@@ -17,6 +17,13 @@ done
 echo "== ncu --set full of variant 11"; date
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:bimamba_scan_fwd_v11 -s 2 -c 1 -f -o gpurun_out/r2_scan_v11 \
     python scripts/time_scan_variants.py --model ps --variants 11 --iters 1 > gpurun_out/r2_ncu_v11.log 2>&1
+echo "== ncu --set full of the lane = channel kernel (variant 20, pass A at 37 segments) through the Python-free probe"; date
+timeout 240 ncu --set full --clock-control none --import-source on --target-processes all -k regex:bimamba_scan_fwd_v20 -s 2 -c 1 -f \
+    -o gpurun_out/r2_scan_v20 ./scripts/_bin/hw_probe 131072 D > gpurun_out/r2_ncu_v20.log 2>&1
+echo "== bench with the scan forced to variant 20 / 22"; date
+for v in 20 22; do
+  timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --scan-variant $v | tee gpurun_out/r2_bench_ps_scan_v$v.json
+done
 echo "== full GPU suite with the scan defaulting to variant 11 where it applies"; date
 CAD_RUN_UNMEASURED=1 CAD_SCAN_VARIANT=11 timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 date
