@@ -5,6 +5,7 @@ path is in csrc/*.cu.  Every function raises RuntimeError on non-CUDA tensors โ
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -14,11 +15,15 @@ from ._lib import CAD_BF16, CAD_F16, CAD_F32
 _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
-SCAN_TOKENS_PER_LANE = 0   # 0 = library default; 8 / 16 force the scan's tokens per lane (tuning knob)
-SCAN_VARIANT = int(__import__("os").environ.get("CAD_SCAN_VARIANT", "0"))   # 0 = library default; 3 / 4 / 7 / 9..12: see cad_scan_fwd_args.variant
-SCAN_NSEG = int(__import__("os").environ.get("CAD_SCAN_NSEG", "0"))   # variant 20: time segments per job (0 = pick from the grid)
-SCAN_DT_IN_XPROJ = __import__("os").environ.get("CAD_DT_IN_XPROJ", "0") == "1"   # variants 9..12: dt = softplus(.) leaves conv_xproj as fp16
-SCAN_BWD_VARIANT = int(__import__("os").environ.get("CAD_SCAN_BWD_VARIANT", "0"))   # 0 = library default; 1 / 2: see cad_scan_bwd_args.variant
+
+# Tuning knobs (module globals so that bench.py / tests can flip them; the environment only sets the initial value).
+# Every value 0 / unset means "library default"; the variants are described at cad_scan_fwd_args.variant /
+# cad_scan_bwd_args.variant in include/caduceus_b200.h and measured in DESIGN.md ยง4.1.
+SCAN_TOKENS_PER_LANE = 0                                            # 8 / 16: tokens per lane of scan variant 3
+SCAN_VARIANT = int(os.environ.get("CAD_SCAN_VARIANT", "0"))         # forward scan: 3, 4, 7, 9..12, 20..23
+SCAN_NSEG = int(os.environ.get("CAD_SCAN_NSEG", "0"))               # variants 20..23: time segments per job
+SCAN_DT_IN_XPROJ = os.environ.get("CAD_DT_IN_XPROJ", "0") == "1"    # variants 9..12: conv_xproj emits dt = softplus(.) as fp16
+SCAN_BWD_VARIANT = int(os.environ.get("CAD_SCAN_BWD_VARIANT", "0"))  # backward scan: 1, 2
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
 
