@@ -338,7 +338,7 @@ static int group_v20(int64_t L) {
   cad_scan_fwd_args r = fwd_args(p, 3, false, p.out_ref);
   if (cad_bimamba_scan_fwd(&r, nullptr)) { say("D: v3 reference failed: %s", cad_last_error()); return 1; }
   float *bcT, *seg_state, *seg_dtsum, *carry;
-  const int max_seg = 64;
+  const int max_seg = 128;
   CK(cudaMalloc(&bcT, (size_t)p.njobs * Lp * 2 * N * 4));
   CK(cudaMalloc(&seg_state, (size_t)p.njobs * max_seg * E * N * 4));
   CK(cudaMalloc(&carry, (size_t)p.njobs * max_seg * E * N * 4));
