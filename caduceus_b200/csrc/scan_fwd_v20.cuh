@@ -85,7 +85,9 @@ struct Smem {
   uint32_t cnt;         // [2] arrival counters of the chunk buffers
   uint64_t* bar;        // full[2]
 };
-inline size_t smem_bytes(int W) { return 1024 + (size_t)2 * kTileBytes + (size_t)W * kStages * kStageBytes + 64; }
+// no swizzled TMA tile here: 128-byte alignment is enough, and at 8 warps the 1 KB slack of the other variants would push two
+// CTAs (2 x (dynamic + 1 KB reserved)) 128 bytes over the 228 KB of an SM
+inline size_t smem_bytes(int W) { return 128 + (size_t)2 * kTileBytes + (size_t)W * kStages * kStageBytes + 64; }
 
 CAD_DEV void carve(unsigned char* base, int W, Smem& sm) {
   const uint32_t b = smem_u32(base);
@@ -276,7 +278,7 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
 
 template <typename T, int NPOLY>
 CAD_DEV void kernel_body(const cad_scan_fwd_args& a, unsigned char* smem_raw) {
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   Smem sm;
   carve(base, CAD_NTHREADS >> 5, sm);
   if (CAD_TID == 0) {
