@@ -106,7 +106,7 @@ class ConvXprojArgs(C.Structure):
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
                 ("delta", _p), ("bc", _p),
                 ("L", _i64), ("E", _i64), ("N", _i64), ("R", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64),
-                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bc16", _p), ("ldbc16", _i64), ("dt_b", _p)]
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bc16", _p), ("ldbc16", _i64), ("dt_b", _p), ("bcT", _p), ("ldT", _i64)]
 
 
 class ConvFwdArgs(C.Structure):

@@ -240,6 +240,11 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
             if (t + 1 < a.ldbc) *reinterpret_cast<float2*>(dst) = make_float2(t < L ? v0 : 0.f, t + 1 < L ? v1 : 0.f);
             else dst[0] = t < L ? v0 : 0.f;
           }
+          if (a.bcT) {                         // the same values token-major: what the lane = channel scan (variants 20..23) reads
+            float* dT = a.bcT + ((int64_t)job * a.ldT + t) * (2 * N) + (r - R);
+            if (t < a.ldT) dT[0] = t < L ? v0 : 0.f;
+            if (t + 1 < a.ldT) dT[2 * N] = t + 1 < L ? v1 : 0.f;
+          }
           if (a.bc16 && t < a.ldbc16) {        // the same rows in the io dtype: tile source of scan variants 9 / 10
             T* d16 = static_cast<T*>(a.bc16) + ((int64_t)job * 2 * N + (r - R)) * a.ldbc16 + t;
             if (t + 1 < a.ldbc16) *reinterpret_cast<uint32_t*>(d16) = pack2<T>(t < L ? v0 : 0.f, t + 1 < L ? v1 : 0.f);
@@ -312,6 +317,7 @@ extern "C" int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream_) {
               a->ldbc % 2 == 0, "cad_conv_xproj_fwd: alignment");
   CAD_REQUIRE(!a->bc16 || (((uintptr_t)a->bc16 & 3) == 0 && a->ldbc16 % 2 == 0 && a->ldbc16 >= a->L),
               "cad_conv_xproj_fwd: bc16 must be 4-byte aligned with an even pitch >= L");
+  CAD_REQUIRE(!a->bcT || (aligned16(a->bcT) && a->ldT >= a->L), "cad_conv_xproj_fwd: bcT must be 16-byte aligned with ldT >= L");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   static_assert(2 * KC * XP >= 8 * 16 * UP, "output staging must fit in the x slabs it aliases");
   const size_t smem = sizeof(uint16_t) * ((size_t)2 * KC * XP + 2 * MROWS * WP + KC * UP + (size_t)a->E * DP + 16 * UP) +

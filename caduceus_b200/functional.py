@@ -261,11 +261,12 @@ def conv_xproj_supported(xz, N, R):
     return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 1024
 
 
-def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=False, dt_b=None):
+def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=False, dt_b=None, want_bcT=False):
     """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores: returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32)
     without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.  want_bc16: also return the
     B / C rows in the activation dtype (njobs, 2N, ceil64(L)) — the tile source of scan variants 9 / 10.
-    dt_b (P, E) fp32: `delta` then holds dt = softplus(dt_raw + dt_b) as FP16 bits (scan_fwd(..., delta_is_dt=True))."""
+    dt_b (P, E) fp32: `delta` then holds dt = softplus(dt_raw + dt_b) as FP16 bits (scan_fwd(..., delta_is_dt=True)).
+    want_bcT: also return the B / C rows token-major, (njobs, ceil256(L), 2N) fp32 — what scan variants 20..23 read."""
     lib = _lib.load()
     seq, pset, rev = jobs
     nseq, twoE, ld = xz.shape
@@ -280,10 +281,18 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=Fal
     a = _lib.ConvXprojArgs(_ptr(xz), _ptr(w_x.contiguous()), _ptr(w_dt.contiguous()), _ptr(conv_w4), _ptr(conv_b),
                            _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(delta), _ptr(bc),
                            L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), _ptr(bc16), bc16.stride(1) if want_bc16 else 0,
-                           _ptr(dt_b))
+                           _ptr(dt_b), None, 0)
+    bcT = None
+    if want_bcT:
+        Lp, L128 = round_up(max(L, 1), 256), round_up(max(L, 1), 128)
+        bcT = torch.empty(njobs, Lp, 2 * N, device=xz.device, dtype=torch.float32)
+        if Lp > L128:
+            bcT[:, L128:].zero_()                 # rows no 128-token tile of the kernel covers
+        a.bcT, a.ldT = _ptr(bcT), Lp
     _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
     _launched()
-    return (delta, bc, bc16) if want_bc16 else (delta, bc)
+    out = (delta, bc, bc16) if want_bc16 else (delta, bc)
+    return out + (bcT,) if want_bcT else out
 
 
 def project_dt_bc(xdbl, dt_w_job, L, N):
@@ -300,7 +309,7 @@ def project_dt_bc(xdbl, dt_w_job, L, N):
 
 def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
              channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None, bc16=None, delta_is_dt=False,
-             nseg=None):
+             nseg=None, bcT=None):
     """Launch the fused bidirectional scan.
     xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld).
     nseg: time segments per job for variant 20 (None = SCAN_NSEG / a grid of about two CTAs per SM)."""
@@ -329,7 +338,8 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     if a.variant in (20, 21, 22, 23):
         if halo is not None or h0 is not None or want_state or want_chunk_state or state_only:
             raise RuntimeError("scan variant 20 covers inference only (no halo / h0 / states)")
-        return scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=nseg, warps_per_cta=channels_per_cta), None, None, None
+        return scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=nseg, warps_per_cta=channels_per_cta,
+                                  bcT=bcT), None, None, None
     if a.variant in (9, 10):
         # 16-bit copy of the B / C rows for the 16-bit-tile kernels (experimental path: a cast per call until the
         # conv_xproj kernel writes it directly); columns [L, ldbc16) must be zero
@@ -360,7 +370,7 @@ def default_nseg(njobs, E, L, warps_per_cta=8):
     return max(1, min(want, L // 2048))
 
 
-def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-24.0):
+def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-24.0, bcT=None):
     """Scan variant 20 (lane = channel, csrc/scan_fwd_v20.cuh): token-major copy of B / C, every segment scanned from a zero
     state, carries composed (cad_seg_carry) and added in place by the segment mode of the fix-up kernel.  `a` is the
     marshalled argument block of scan_fwd (reused so that the two paths cannot drift apart).  cutoff_log2: a carry term is
@@ -375,8 +385,11 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     W = warps_per_cta if warps_per_cta > 0 else min(8 if njobs >= 4 else 4 if njobs >= 2 else 2, (E + 31) // 32)
     nseg = default_nseg(njobs, E, L, W) if nseg is None else int(nseg)
     Lp = round_up(max(L, 1), 256)
-    bcT = torch.empty(njobs, Lp, twoN, device=dev, dtype=torch.float32)
-    _lib.check(lib.cad_bc_transpose(_ptr(bc), _ptr(bcT), njobs, twoN, L, ldbc, _stream()), "cad_bc_transpose")
+    if bcT is None:                               # conv_xproj(want_bcT=True) writes it directly; otherwise one transpose launch
+        bcT = torch.empty(njobs, Lp, twoN, device=dev, dtype=torch.float32)
+        _lib.check(lib.cad_bc_transpose(_ptr(bc), _ptr(bcT), njobs, twoN, L, ldbc, _stream()), "cad_bc_transpose")
+        _launched()
+    assert bcT.shape == (njobs, Lp, twoN) and bcT.is_contiguous()
     seg_state = torch.empty(njobs, nseg, E, N, device=dev, dtype=torch.float32)
     seg_dtsum = torch.empty(njobs, nseg, E, device=dev, dtype=torch.float32)
     a.bcT, a.nseg, a.seg_state, a.seg_dtsum, a.channels_per_cta = _ptr(bcT), nseg, _ptr(seg_state), _ptr(seg_dtsum), W
@@ -385,7 +398,7 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     _lib.check(lib.cad_bimamba_scan_fwd(C.byref(a), _stream()), "cad_bimamba_scan_fwd")
-    _launched(2)
+    _launched()
     if nseg > 1:
         carry = torch.empty(njobs, nseg, E, N, device=dev, dtype=torch.float32)
         _lib.check(lib.cad_seg_carry(_ptr(seg_state), _ptr(seg_dtsum), _ptr(A2), _ptr(pset), _ptr(carry), njobs, nseg, E,

@@ -262,13 +262,16 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
         # inference only: the fix-up kernel of the sharded path and the backward need dt_raw)
         dt_ready = CF.SCAN_DT_IN_XPROJ and CF.SCAN_VARIANT in (9, 10, 11, 12) and not sharded
         dt_b = packed[2] if dt_ready else None
-        if CF.SCAN_VARIANT in (9, 10):     # 16-bit-tile scan variants: the tile source comes straight from this kernel
+        bcT = None
+        if CF.SCAN_VARIANT in (20, 21, 22, 23) and not sharded:   # lane = channel scan: B / C token-major from the same kernel
+            delta, bc, bcT = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo, want_bcT=True)
+        elif CF.SCAN_VARIANT in (9, 10):     # 16-bit-tile scan variants: the tile source comes straight from this kernel
             delta, bc, bc16 = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo,
                                             want_bc16=True, dt_b=dt_b)
         else:
             delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo, dt_b=dt_b)
     else:
-        bc16, dt_ready = None, False
+        bc16, bcT, dt_ready = None, None, False
         u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                    # (njobs, E, Lp)
         wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
         xdbl = torch.bmm(wx_job, u)                                                       # (njobs, R+2N, Lp)
@@ -279,7 +282,7 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
 
     # ---- fused scan --------------------------------------------------------------------------------------
     if not sharded:
-        yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, bc16=bc16, delta_is_dt=dt_ready)
+        yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, bc16=bc16, delta_is_dt=dt_ready, bcT=bcT)
     else:
         # zero-carry scan (outputs + end state + sum dt) -> ONE all_gather -> compose this shard's carry-in ->
         # add its decaying contribution in place (seqshard.py, csrc/scan_fixup.cu).  Ranks never wait for each other.

@@ -274,6 +274,9 @@ typedef struct {
   void* bc16; int64_t ldbc16;
   const float* dt_b;        /* optional (NULL): (P, E) dt bias; when set, `delta` receives dt = softplus(round_io(dt_raw)
                                + dt_b) as FP16 instead of dt_raw in the io dtype (cad_scan_fwd_args.delta_is_dt) */
+  float* bcT;               /* optional (NULL): (njobs, ldT, 2N) fp32, the B / C rows TOKEN-major (scan variants 20..23), written for
+                               tokens [0, min(ldT, ceil128(L))), zeros from L on; the caller zero-fills rows beyond ceil128(L) */
+  int64_t ldT;              /* rows per job of bcT (ceil256(L)) */
 } cad_conv_xproj_args;
 int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
 

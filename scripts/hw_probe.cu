@@ -306,6 +306,24 @@ static int group_xproj(int64_t L) {
   CK(cudaDeviceSynchronize());
   make_dt16<<<1184, 256>>>(p.delta, p.dt_b, p.pset, dt_ref, E, L, n_tok);
   f32_to_bf16<<<1184, 256>>>(p.bc, bc16_ref, n_bc);
+  // token-major B / C straight from the kernel (scan variants 20..23) against the transpose of its own state-major rows
+  {
+    const int64_t Lp = (L + 255) / 256 * 256;
+    float *bcT_k, *bcT_t;
+    CK(cudaMalloc(&bcT_k, (size_t)n_bc / L * Lp * 4)); CK(cudaMalloc(&bcT_t, (size_t)n_bc / L * Lp * 4));
+    CK(cudaMemset(bcT_k, 0, (size_t)n_bc / L * Lp * 4));
+    cad_conv_xproj_args t = a;
+    t.bcT = bcT_k; t.ldT = Lp;
+    if (cad_conv_xproj_fwd(&t, nullptr)) { say("C: conv_xproj (bcT) failed: %s", cad_last_error()); return 1; }
+    if (cad_bc_transpose(p.bc, bcT_t, p.njobs, 2 * N, L, L, nullptr)) { say("C: cad_bc_transpose failed: %s", cad_last_error()); return 1; }
+    Cmp ct;
+    if (cmp<float>(bcT_k, bcT_t, n_bc / L * Lp, p.stats, &ct)) return 1;
+    say("C: bcT from conv_xproj vs cad_bc_transpose(bc)           max|diff| %.3e  max|ref| %.3e  non-finite %u", ct.maxdiff, ct.maxref, ct.bad);
+    float tt, ttm;
+    if (time_launches([&]() { return cad_conv_xproj_fwd(&t, nullptr); }, 1, 4, &tt, &ttm)) return 1;
+    say("C: conv_xproj + bcT  min %.3f mean %.3f ms", tt, ttm);
+    cudaFree(bcT_k); cudaFree(bcT_t);
+  }
   cad_conv_xproj_args b = a;
   b.delta = delta_b; b.bc = bc_b; b.bc16 = p.bc16; b.ldbc16 = L; b.dt_b = p.dt_b;
   CK(cudaMemset(delta_b, 0xFF, (size_t)n_tok * 2)); CK(cudaMemset(p.bc16, 0xFF, (size_t)n_bc * 2));

@@ -201,6 +201,9 @@ def test_conv_xproj_dt_epilogue_matches_softplus_of_its_own_dt_raw(dtype):
     raw, bc0 = CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L)
     dt16, bc1 = CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, dt_b=dt_b)
     assert torch.equal(bc0, bc1)
+    _, bc2, bcT = CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, want_bcT=True)     # token-major copy, variants 20..23
+    assert torch.equal(bc0, bc2) and bcT.shape == (4, 1536, 2 * N)
+    assert torch.equal(bcT[:, :L], bc0[..., :L].transpose(1, 2)) and (bcT[:, L:] == 0).all()
     got = (dt16 if dtype == torch.float16 else dt16.view(torch.float16))[..., :L].float()
     want = torch.nn.functional.softplus(raw[..., :L].float() + dt_b[jobs[1].long()][:, :, None])
     assert torch.isfinite(got).all()
