@@ -198,3 +198,19 @@ def test_argument_marshalling_and_validation_reach_the_library_without_a_gpu(mon
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=3, delta_is_dt=True)
     with pytest.raises(RuntimeError, match="cad_bimamba_scan_fwd failed .*cuTensorMapEncodeTiled"):
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=12, delta_is_dt=True)
+
+
+def test_segment_count_of_the_lane_per_channel_scan():
+    """variants 20..23: about two CTAs per SM (148 SMs when no device is visible), whole 256-token chunks, no segment shorter
+    than 2048 tokens; CAD_SCAN_NSEG overrides."""
+    from caduceus_b200 import functional as CF
+    assert CF.default_nseg(4, 512, 131072, 8) == 37          # Caduceus-PS headline: 4 jobs x 2 channel groups x 37 = 296 CTAs
+    assert CF.default_nseg(2, 512, 131072, 4) == 37          # Caduceus-Ph: 2 jobs x 4 groups x 37
+    assert CF.default_nseg(4, 512, 4096, 8) == 2 and CF.default_nseg(4, 512, 1024, 8) == 1
+    assert CF.default_nseg(64, 512, 131072, 8) == 2          # a large batch needs almost no time split
+    old = CF.SCAN_NSEG
+    try:
+        CF.SCAN_NSEG = 9
+        assert CF.default_nseg(4, 512, 131072, 8) == 9
+    finally:
+        CF.SCAN_NSEG = old
