@@ -10,6 +10,7 @@
 #include "../../caduceus_b200/csrc/scan_fwd_v9.cuh"
 #include "../../caduceus_b200/csrc/scan_bwd_v2.cuh"
 #include "../../caduceus_b200/csrc/scan_fwd_v20.cuh"
+#include "../../caduceus_b200/csrc/scan_fixup.cuh"
 
 namespace cad {
 thread_local EmuThread g_t;
@@ -152,5 +153,29 @@ extern "C" int emu_scan_v20(const cad_scan_fwd_args* a, int W) {
         if (a->io_dtype == CAD_BF16) run_v20<__nv_bfloat16>(a, sb, W, bx, by, bz);
         else run_v20<__half>(a, sb, W, bx, by, bz);
       }
+  return 0;
+}
+
+// carry fix-up (scan_fixup.cuh): whole-sequence mode (grid.y = jobs) or segment mode (grid.y = jobs x (nseg - 1))
+extern "C" int emu_scan_fixup(const cad_scan_fixup_args* a, int G) {
+  using namespace cad;
+  if (a->N != 16 || G < 1 || G > fx::kMaxG || a->ldbc % 32) return -1;
+  if (a->L <= 0) return 0;
+  EmuTmap tmap;
+  tmap.base = a->bc;
+  tmap.elem_bytes = 4;
+  tmap.nrows = (int64_t)a->njobs * 32;
+  tmap.ld = a->ldbc;
+  tmap.nblk = (a->L + 31) / 32;
+  tmap.box_blocks = fx::kChunk / 32;
+  tmap.box_rows = 16;
+  const int gx = (int)((a->E + G - 1) / G), gy = a->nseg > 1 ? a->njobs * (a->nseg - 1) : a->njobs;
+  const size_t sb = 1024 + (size_t)16 * fx::kChunk * 4 + (size_t)2 * fx::kMaxG * 16 * 4 + 16;
+  for (int by = 0; by < gy; ++by)
+    for (int bx = 0; bx < gx; ++bx) {
+      if (a->io_dtype == CAD_BF16) run_cta(sb, G, bx, by, [&](unsigned char* sm) { fx::kernel_body<__nv_bfloat16, 16>(*a, &tmap, sm); });
+      else if (a->io_dtype == CAD_F16) run_cta(sb, G, bx, by, [&](unsigned char* sm) { fx::kernel_body<__half, 16>(*a, &tmap, sm); });
+      else run_cta(sb, G, bx, by, [&](unsigned char* sm) { fx::kernel_body<float, 16>(*a, &tmap, sm); });
+    }
   return 0;
 }

@@ -13,6 +13,7 @@
 #include <string.h>
 #include <math.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -67,9 +68,10 @@ struct EmuCta {
   std::condition_variable cv;
   std::map<const void*, Mbar> mbars;
   bool deadlock = false;
+  std::atomic<int> or_flag[2] = {{0}, {0}};   // __syncthreads_or: alternating per call
 };
 
-struct EmuThread { EmuCta* cta; int tid, bx, by, bz = 0; };
+struct EmuThread { EmuCta* cta; int tid, bx, by, bz = 0; int or_epoch = 0; };
 extern thread_local EmuThread g_t;
 
 namespace v4 {
@@ -246,6 +248,31 @@ inline void stg128f(float* p, float a, float b, float c, float d) {
   p[0] = a; p[1] = b; p[2] = c; p[3] = d;
 }
 }  // namespace v20
+
+namespace fx {        // scan_fixup.cuh
+constexpr int kTok = 16, kChunk = 512, kMaxG = 7;
+// __syncthreads_or: two flags used alternately; thread 0 clears the one just read before it can reach the call after next
+inline bool cta_sync_or(bool p) {
+  EmuCta* c = g_t.cta;
+  const int e = g_t.or_epoch++ & 1;
+  if (p) c->or_flag[e].store(1);
+  pthread_barrier_wait(&c->cta_bar);
+  const bool r = c->or_flag[e].load() != 0;
+  pthread_barrier_wait(&c->cta_bar);
+  if (g_t.tid == 0) c->or_flag[e].store(0);
+  return r;
+}
+template <typename T, int V>
+inline void load_vec(const T* p, float (&v)[V]) {
+  if ((uintptr_t)p & 15) { fprintf(stderr, "emu: misaligned vector load\n"); abort(); }
+  for (int i = 0; i < V; ++i) v[i] = io<T>::to_f(p[i]);
+}
+template <typename T, int V>
+inline void store_vec(T* p, const float (&v)[V]) {
+  if ((uintptr_t)p & 15) { fprintf(stderr, "emu: misaligned vector store\n"); abort(); }
+  for (int i = 0; i < V; ++i) p[i] = io<T>::from_f(v[i]);
+}
+}  // namespace fx
 
 namespace bw2 {
 inline float shfl_down1(float v, int off) { const int l = g_t.tid & 31; return v4::shfl_raw(v, l + off < 32 ? l + off : l); }

@@ -28,7 +28,8 @@ def emu():
         os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fwd_v4.cuh"),
         os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fwd_v9.cuh"),
         os.path.join(ROOT, "caduceus_b200", "csrc", "scan_bwd_v2.cuh"),
-        os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fwd_v20.cuh"), os.path.join(ROOT, "include", "caduceus_b200.h")]
+        os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fwd_v20.cuh"),
+        os.path.join(ROOT, "caduceus_b200", "csrc", "scan_fixup.cuh"), os.path.join(ROOT, "include", "caduceus_b200.h")]
     if not os.path.exists(os.path.join(CUDA_INC, "cuda_bf16.h")):
         pytest.skip("CUDA headers not found")
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
@@ -41,6 +42,8 @@ def emu():
     lib.emu_scan_v9.argtypes = [C.POINTER(_lib.ScanFwdArgs), C.c_int, C.c_int, C.c_int]
     lib.emu_scan_v20.restype = C.c_int
     lib.emu_scan_v20.argtypes = [C.POINTER(_lib.ScanFwdArgs), C.c_int]
+    lib.emu_scan_fixup.restype = C.c_int
+    lib.emu_scan_fixup.argtypes = [C.POINTER(_lib.ScanFixupArgs), C.c_int]
     lib.emu_scan_bwd_v2.restype = C.c_int
     lib.emu_scan_bwd_v2.argtypes = [C.POINTER(_lib.ScanBwdArgs), C.c_int]
     return lib
