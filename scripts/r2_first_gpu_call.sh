@@ -24,6 +24,10 @@ echo "== bench with the scan forced to variant 20 / 22"; date
 for v in 20 22; do
   timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --scan-variant $v | tee gpurun_out/r2_bench_ps_scan_v$v.json
 done
+echo "== Caduceus-Ph bench under 3 / 12 / 20"; date
+for v in 3 12 20; do
+  timeout 200 python bench.py --model ph --steps 5 --warmup 3 --no-cpu-baseline --scan-variant $v | tee gpurun_out/r2_bench_ph_scan_v$v.json
+done
 echo "== full GPU suite with the scan defaulting to variant 11 where it applies"; date
 CAD_RUN_UNMEASURED=1 CAD_SCAN_VARIANT=11 timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -8
 date
