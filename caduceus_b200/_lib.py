@@ -62,7 +62,7 @@ class ScanFixupArgs(C.Structure):
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("h0", _p),
                 ("L", _i64), ("E", _i64), ("N", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
                 ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
-                ("cutoff_log2", _f32), ("nseg", _i32), ("seg_carry", _p)]
+                ("cutoff_log2", _f32), ("nseg", _i32), ("seg_carry", _p), ("seg_first", _i32)]
 
 
 class ScanAdjointArgs(C.Structure):
@@ -135,7 +135,7 @@ SYMBOLS = {
     "cad_conv_xproj_fwd": (C.c_int, [C.POINTER(ConvXprojArgs), _p]),
     "cad_bimamba_scan_adjoint": (C.c_int, [C.POINTER(ScanAdjointArgs), _p]),
     "cad_bc_transpose": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
-    "cad_seg_carry": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
+    "cad_seg_carry": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
     "cad_hg38_batch_fwd": (C.c_int, [C.POINTER(Hg38BatchArgs), _p]),
     "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),
 }

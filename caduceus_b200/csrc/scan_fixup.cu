@@ -18,7 +18,7 @@ static int launch_fixup(const cad_scan_fixup_args& a, int G, cudaStream_t stream
   auto kern = scan_fixup_kernel<T, N>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)(a.nseg > 1 ? a.njobs * (a.nseg - 1) : a.njobs));
+  dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)(a.nseg > 1 ? a.njobs * (a.nseg - (a.seg_first ? 0 : 1)) : a.njobs));
   kern<<<grid, G * 32, smem, stream>>>(a, tmap);
   CAD_LAUNCH_CHECK();
   return 0;

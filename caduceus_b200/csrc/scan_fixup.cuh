@@ -174,8 +174,9 @@ CAD_DEV void kernel_body(const cad_scan_fixup_args& a, const tmap_t* tmap, unsig
   if (a.nseg > 1) {
     // grid.y = (job, logical segment s >= 1); the segment's tokens = physical block k of the split used by scan variant 20
     // (scan_fwd_v20.cuh::block_range: whole 256-token chunks, ceil(nchunks / nseg) per block)
-    const int sl = 1 + (int)(CAD_BIDY % (a.nseg - 1));
-    job = (int)(CAD_BIDY / (a.nseg - 1));
+    const int first = a.seg_first ? 0 : 1, cnt = a.nseg - first;      // logical segments [first, nseg) get a carry term
+    const int sl = first + (int)(CAD_BIDY % cnt);
+    job = (int)(CAD_BIDY / cnt);
     const int64_t k = a.rev_of_job[job] ? a.nseg - 1 - sl : sl;
     const int64_t nch = (a.L + 255) / 256, per = (nch + a.nseg - 1) / a.nseg;
     int64_t lo = k * per * 256, hi = (k + 1) * per * 256;

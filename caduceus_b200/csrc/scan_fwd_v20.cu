@@ -24,9 +24,9 @@ static auto v20_kernel_for(int npoly) -> void (*)(const cad_scan_fwd_args) {
 int launch_scan_v20(const cad_scan_fwd_args& a, cudaStream_t stream) {
   const int nseg = a.nseg > 0 ? a.nseg : 1;
   CAD_REQUIRE(a.io_dtype != CAD_F32, "cad_bimamba_scan_fwd: variant 20 needs 16-bit I/O");
-  CAD_REQUIRE(!a.halo && !a.h0 && !a.hlast && !a.dtsum && !a.chunk_state && !a.state_only,
-              "cad_bimamba_scan_fwd: variant 20 covers inference only (none of halo / h0 / hlast / dtsum / chunk_state / "
-              "state_only)");
+  CAD_REQUIRE(!a.h0 && !a.hlast && !a.dtsum && !a.chunk_state && !a.state_only,
+              "cad_bimamba_scan_fwd: variant 20 covers inference only (no chunk_state / state_only; carry-in, end state and "
+              "sum dt come from cad_seg_carry on the segment outputs, not from this launch)");
   CAD_REQUIRE(a.bcT && aligned16(a.bcT), "cad_bimamba_scan_fwd: variant 20 needs bcT (cad_bc_transpose), 16-byte aligned");
   CAD_REQUIRE(nseg <= 4096, "cad_bimamba_scan_fwd: nseg out of range");
   CAD_REQUIRE(nseg == 1 || (a.seg_state && a.seg_dtsum), "cad_bimamba_scan_fwd: nseg > 1 needs seg_state and seg_dtsum");
@@ -77,18 +77,24 @@ __global__ void __launch_bounds__(256) bc_transpose_kernel(const float* __restri
 // carry[j, s, e, n]: state entering logical segment s.  One thread per (job, channel, state); nseg sequential steps.
 __global__ void __launch_bounds__(256) seg_carry_kernel(const float* __restrict__ seg_state, const float* __restrict__ seg_dtsum,
                                                         const float* __restrict__ A2, const int32_t* __restrict__ pset_of_job,
-                                                        float* __restrict__ carry, int64_t njobs, int64_t nseg, int64_t E) {
+                                                        const float* __restrict__ h0, float* __restrict__ carry,
+                                                        float* __restrict__ hlast, float* __restrict__ dtsum, int64_t njobs,
+                                                        int64_t nseg, int64_t E) {
   constexpr int N = 16;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= njobs * E * N) return;
   const int64_t n = i % N, e = (i / N) % E, j = i / (N * E);
   const float a2 = A2[((int64_t)pset_of_job[j] * E + e) * N + n];
-  float h = 0.f;
+  float h = h0 ? h0[(j * E + e) * N + n] : 0.f, dsum = 0.f;
   for (int64_t s = 0; s < nseg; ++s) {
     const int64_t row = (j * nseg + s) * E + e;
-    carry[row * N + n] = h;
-    h = fmaf(ex2(a2 * seg_dtsum[row]), h, seg_state[row * N + n]);
+    if (carry) carry[row * N + n] = h;
+    const float ds = seg_dtsum[row];
+    dsum += ds;
+    h = fmaf(ex2(a2 * ds), h, seg_state[row * N + n]);
   }
+  if (hlast) hlast[(j * E + e) * N + n] = h;
+  if (dtsum && n == 0) dtsum[j * E + e] = dsum;
 }
 
 }  // namespace cad
@@ -105,13 +111,14 @@ extern "C" int cad_bc_transpose(const float* bc, float* bcT, int64_t njobs, int6
 }
 
 extern "C" int cad_seg_carry(const float* seg_state, const float* seg_dtsum, const float* A2, const int32_t* pset_of_job,
-                             float* carry, int64_t njobs, int64_t nseg, int64_t E, void* stream_) {
+                             const float* h0, float* carry, float* hlast, float* dtsum, int64_t njobs, int64_t nseg, int64_t E,
+                             void* stream_) {
   using namespace cad;
-  CAD_REQUIRE(seg_state && seg_dtsum && A2 && pset_of_job && carry && njobs > 0 && nseg > 0 && E > 0,
+  CAD_REQUIRE(seg_state && seg_dtsum && A2 && pset_of_job && (carry || hlast || dtsum) && njobs > 0 && nseg > 0 && E > 0,
               "cad_seg_carry: bad arguments");
   const int64_t n = njobs * E * 16;
-  seg_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(seg_state, seg_dtsum, A2,
-                                                                                                 pset_of_job, carry, njobs, nseg, E);
+  seg_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      seg_state, seg_dtsum, A2, pset_of_job, h0, carry, hlast, dtsum, njobs, nseg, E);
   CAD_LAUNCH_CHECK();
   return 0;
 }

@@ -20,8 +20,8 @@
 // The price is that a channel has no time parallelism any more: one GPU must cut the sequence into `nseg` segments per job
 // (grid.z), scan each from a ZERO state (this kernel: outputs, end state and sum dt of every segment) and resolve the carries
 // afterwards exactly like the multi-GPU path does: cad_seg_carry composes the carry-in of every segment,
-// cad_bimamba_scan_fixup adds its decaying contribution in place.  Inference only (no conv halo / carry-in / saved chunk
-// states), 16-bit I/O.  Written against the SIMT primitives of scan_fwd_v4/v9.cuh so that tests/emu/ compiles THIS file
+// cad_bimamba_scan_fixup adds its decaying contribution in place.  Inference only (no saved chunk states), 16-bit I/O; the
+// sharding hooks are served by the same machinery: conv halo here, carry-in / end state / sum dt by cad_seg_carry.  Written against the SIMT primitives of scan_fwd_v4/v9.cuh so that tests/emu/ compiles THIS file
 // for the host.
 #pragma once
 #include <type_traits>
@@ -139,8 +139,14 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) A2p[p] = make_float2(a.A2[pc * NST + 2 * p], a.A2[pc * NST + 2 * p + 1]);
 
-    // the three x values that logically precede the block (zero outside the sequence: no conv halo in this variant)
-    auto x_at = [&](int64_t t) -> float { return (t >= 0 && t < L) ? io<T>::to_f(xrow[t]) : 0.f; };
+    // x outside the sequence: the conv halo (x at logical times -3, -2, -1: sequence sharding) before logical time 0, else zero
+    float hal0 = 0.f, hal1 = 0.f, hal2 = 0.f;
+    if (a.halo) {
+      const T* hp = static_cast<const T*>(a.halo) + ((int64_t)job * E + chc) * 3;
+      hal0 = io<T>::to_f(hp[0]); hal1 = io<T>::to_f(hp[1]); hal2 = io<T>::to_f(hp[2]);
+    }
+    auto halo_at = [&](int64_t tau) -> float { return tau == -1 ? hal2 : (tau == -2 ? hal1 : (tau == -3 ? hal0 : 0.f)); };
+    auto x_at = [&](int64_t t) -> float { return (t >= 0 && t < L) ? io<T>::to_f(xrow[t]) : halo_at(REV ? L - 1 - t : t); };
     float w0, w1, w2;
     if (REV) { w0 = x_at(t_hi + 2); w1 = x_at(t_hi + 1); w2 = x_at(t_hi); }
     else     { w0 = x_at(t_lo - 3); w1 = x_at(t_lo - 2); w2 = x_at(t_lo - 1); }
@@ -202,7 +208,8 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
       for (int i = 0; i < GT; ++i) {
         const int pi = REV ? GT - 1 - i : i;                  // physical position inside the group
         const bool masked = TAIL && (t0 + pi >= L);
-        const float xv = masked ? 0.f : io<T>::to_f(xe[pi]);
+        // a masked token of a reversed job lies logically BEFORE the sequence: it feeds the conv window with the halo
+        const float xv = masked ? (REV ? halo_at(L - 1 - (t0 + pi)) : 0.f) : io<T>::to_f(xe[pi]);
         const float cv = cb + cw0 * w0 + cw1 * w1 + cw2 * w2 + cw3 * xv;
         w0 = w1; w1 = w2; w2 = xv;
         const float u = silu_io<T>(cv);

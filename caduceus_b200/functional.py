@@ -336,10 +336,13 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
         SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0, None, 0, int(delta_is_dt))
     a.variant = scan_variant(a) if variant is None else int(variant)
     if a.variant in (20, 21, 22, 23):
-        if halo is not None or h0 is not None or want_state or want_chunk_state or state_only:
-            raise RuntimeError("scan variant 20 covers inference only (no halo / h0 / states)")
+        if h0 is not None or want_chunk_state or state_only:
+            raise RuntimeError("scan variant 20 covers inference only (no carry-in at launch, saved chunk states or state-only "
+                               "pass; a sequence shard takes its carry-in through scan_fixup(..., seg_ctx=...))")
+        # the kernel itself produces neither end state nor sum dt: they are composed from the segment outputs
+        a.hlast, a.dtsum = None, None
         return scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=nseg, warps_per_cta=channels_per_cta,
-                                  bcT=bcT), None, None, None
+                                  bcT=bcT, want_state=want_state)
     if a.variant in (9, 10):
         # 16-bit copy of the B / C rows for the 16-bit-tile kernels (experimental path: a cast per call until the
         # conv_xproj kernel writes it directly); columns [L, ldbc16) must be zero
@@ -370,12 +373,16 @@ def default_nseg(njobs, E, L, warps_per_cta=8):
     return max(1, min(want, L // 2048))
 
 
-def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-24.0, bcT=None):
+def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-24.0, bcT=None,
+                       want_state=False):
     """Scan variant 20 (lane = channel, csrc/scan_fwd_v20.cuh): token-major copy of B / C, every segment scanned from a zero
     state, carries composed (cad_seg_carry) and added in place by the segment mode of the fix-up kernel.  `a` is the
     marshalled argument block of scan_fwd (reused so that the two paths cannot drift apart).  cutoff_log2: a carry term is
     dropped once its decay factor is below 2^cutoff — 2^-24 is 4 decimal orders under the ulp of the 16-bit outputs this
-    variant is restricted to (the multi-GPU path keeps 2^-40 because it also serves fp32 I/O)."""
+    variant is restricted to (the multi-GPU path keeps 2^-40 because it also serves fp32 I/O).
+    Returns (out, hlast, dtsum, seg_ctx).  want_state (a sequence SHARD): the local carries are NOT applied
+    here; hlast / dtsum are the shard's zero-carry end state and sum dt for the all_gather, and seg_ctx goes to
+    scan_fixup(..., h0, seg_ctx=seg_ctx), which applies the shard's carry-in and the local carries in ONE pass."""
     lib = _lib.load()
     seq, pset, rev = jobs
     conv_w4, conv_b, dt_b, A2, Dk = packed
@@ -399,10 +406,17 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
         ev[0].record()
     _lib.check(lib.cad_bimamba_scan_fwd(C.byref(a), _stream()), "cad_bimamba_scan_fwd")
     _launched()
-    if nseg > 1:
+    hlast = dtsum = None
+    if want_state:
+        hlast = torch.empty(njobs, E, N, device=dev, dtype=torch.float32)
+        dtsum = torch.empty(njobs, E, device=dev, dtype=torch.float32)
+        _lib.check(lib.cad_seg_carry(_ptr(seg_state), _ptr(seg_dtsum), _ptr(A2), _ptr(pset), None, None, _ptr(hlast),
+                                     _ptr(dtsum), njobs, nseg, E, _stream()), "cad_seg_carry")
+        _launched()
+    elif nseg > 1:
         carry = torch.empty(njobs, nseg, E, N, device=dev, dtype=torch.float32)
-        _lib.check(lib.cad_seg_carry(_ptr(seg_state), _ptr(seg_dtsum), _ptr(A2), _ptr(pset), _ptr(carry), njobs, nseg, E,
-                                     _stream()), "cad_seg_carry")
+        _lib.check(lib.cad_seg_carry(_ptr(seg_state), _ptr(seg_dtsum), _ptr(A2), _ptr(pset), None, _ptr(carry), None, None,
+                                     njobs, nseg, E, _stream()), "cad_seg_carry")
         if a.delta_is_dt:
             raise RuntimeError("scan variant 20 with nseg > 1 needs dt_raw (the fix-up kernel applies the softplus itself)")
         f = _lib.ScanFixupArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
@@ -413,7 +427,8 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     if ev is not None:
         ev[1].record()
         SCAN_EVENTS.append(ev)
-    return out
+    seg_ctx = {"nseg": nseg, "seg_state": seg_state, "seg_dtsum": seg_dtsum, "cutoff_log2": cutoff_log2} if want_state else None
+    return out, hlast, dtsum, seg_ctx
 
 
 def scan_variant(a):
@@ -426,13 +441,12 @@ def scan_variant(a):
     if SCAN_VARIANT in (9, 10, 11, 12):
         return SCAN_VARIANT if (a.io_dtype != CAD_F32 and a.N == 16 and a.tokens_per_lane in (0, 16)) else 0
     if SCAN_VARIANT in (20, 21, 22, 23):
-        ok = (a.io_dtype != CAD_F32 and a.N == 16 and not (a.halo or a.h0 or a.hlast or a.dtsum or a.chunk_state)
-              and not a.state_only)
+        ok = a.io_dtype != CAD_F32 and a.N == 16 and not (a.h0 or a.chunk_state) and not a.state_only
         return SCAN_VARIANT if ok else 0
     return SCAN_VARIANT
 
 
-def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, channels_per_cta=0):
+def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, channels_per_cta=0, seg_ctx=None):
     """In place: out += silu(z) * sum_n C * exp2(A2 * cumsum(dt)) * h0 — turns a zero-carry shard scan into the scan
     with carry-in h0 (njobs, E, N).  See csrc/scan_fixup.cu."""
     lib = _lib.load()
@@ -441,9 +455,21 @@ def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, chann
     nseq, twoE, ldxz = xz.shape
     E = twoE // 2
     njobs, twoN, ldbc = bc.shape
+    h0 = h0.contiguous()
     a = _lib.ScanFixupArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
-                           _ptr(rev), _ptr(h0.contiguous()), L, E, twoN // 2, ldxz, delta.stride(1), ldbc, out.stride(1),
+                           _ptr(rev), _ptr(h0), L, E, twoN // 2, ldxz, delta.stride(1), ldbc, out.stride(1),
                            nseq, njobs, _dt(xz), channels_per_cta, float(cutoff_log2))
+    if seg_ctx is not None:
+        # `out` came from scan variant 20 (every segment scanned from zero): compose the carry of every segment from the shard's
+        # carry-in h0 and the segment end states, and fix up ALL segments (the first one included) in this one launch
+        nseg = seg_ctx["nseg"]
+        carry = torch.empty(njobs, nseg, E, twoN // 2, device=xz.device, dtype=torch.float32)
+        _lib.check(lib.cad_seg_carry(_ptr(seg_ctx["seg_state"]), _ptr(seg_ctx["seg_dtsum"]), _ptr(A2), _ptr(pset), _ptr(h0),
+                                     _ptr(carry), None, None, njobs, nseg, E, _stream()), "cad_seg_carry")
+        _launched()
+        if nseg > 1:
+            a.nseg, a.seg_carry, a.seg_first, a.cutoff_log2 = nseg, _ptr(carry), 1, float(seg_ctx["cutoff_log2"])
+        # nseg == 1: carry[:, 0] == h0 and the whole-sequence mode below is exactly what is needed
     _lib.check(lib.cad_bimamba_scan_fixup(C.byref(a), _stream()), "cad_bimamba_scan_fixup")
     _launched()
     return out

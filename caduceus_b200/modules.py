@@ -282,13 +282,14 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
 
     # ---- fused scan --------------------------------------------------------------------------------------
     if not sharded:
-        yg, _, _, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, bc16=bc16, delta_is_dt=dt_ready, bcT=bcT)
+        yg = CF.scan_fwd(xz, delta, bc, packed, jobs, L, bc16=bc16, delta_is_dt=dt_ready, bcT=bcT)[0]
     else:
         # zero-carry scan (outputs + end state + sum dt) -> ONE all_gather -> compose this shard's carry-in ->
         # add its decaying contribution in place (seqshard.py, csrc/scan_fixup.cu).  Ranks never wait for each other.
-        yg, hl, ds, _ = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True, bc16=bc16)
+        # (with scan variant 20 the shard is itself cut into segments: seg_ctx carries their end states to the fix-up)
+        yg, hl, ds, seg_ctx = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True, bc16=bc16)
         h0 = seqshard.gather_carry(hl, ds, packed[3], jobs[1], jobs[2], shard)
-        CF.scan_fixup(xz, delta, bc, yg, packed, jobs, L, h0)
+        CF.scan_fixup(xz, delta, bc, yg, packed, jobs, L, h0, seg_ctx=seg_ctx if isinstance(seg_ctx, dict) else None)
     del xz
 
     # ---- out_proj -------------------------------------------------------------------------------------------

@@ -160,8 +160,8 @@ typedef struct {
                                scan's prologue then has no softplus (2 of its MUFU ops per token and channel) */
   /* variants 20..23 only (lane = channel: a warp owns 32 channels and walks time serially, 16 states per lane as packed pairs,
      B / C as broadcast reads, no shuffles; 21..23 take the exp2 of 1 / 2 / 3 of the 8 state pairs from a polynomial on the FMA
-     pipe instead of MUFU; channels_per_cta then counts WARPS per CTA, <= 8; 16-bit I/O, inference: none of halo / h0 / hlast /
-     dtsum / chunk_state / state_only): */
+     pipe instead of MUFU; channels_per_cta then counts WARPS per CTA, <= 8; 16-bit I/O, inference: no chunk_state /
+     state_only, and h0 / hlast / dtsum go through cad_seg_carry instead of this launch; halo is honoured): */
   const float* bcT;         /* (njobs, ceil256(L), 2N) fp32: the B / C rows TOKEN-major, zeros beyond L (cad_bc_transpose) */
   int32_t nseg;             /* time segments per job (grid.z), whole 256-token chunks each; 0 = 1.  Every segment is scanned
                                from a ZERO state: with nseg > 1 `out` still lacks the carries (cad_seg_carry + cad_bimamba_scan_fixup) */
@@ -174,11 +174,13 @@ int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512)
 /* helpers of scan variant 20 (a sequence cut into nseg segments INSIDE one GPU; same algebra as the multi-GPU path):
  *   cad_bc_transpose: bc (njobs, 2N, ldbc) fp32 -> bcT (njobs, ceil256(L), 2N), zeros in rows [L, ceil256(L)).
  *   cad_seg_carry:    carry[j, s] = state entering logical segment s of job j:
- *                       carry[j, 0] = 0,  carry[j, s+1] = exp2(A2 * seg_dtsum[j, s]) * carry[j, s] + seg_state[j, s]   (N == 16)
- *   the carries are then applied by cad_bimamba_scan_fixup with nseg / seg_carry set.                                      */
+ *                       carry[j, 0] = h0[j] (or 0),  carry[j, s+1] = exp2(A2 * seg_dtsum[j, s]) * carry[j, s] + seg_state[j, s]
+ *                     and, optionally, what a sequence shard hands to its neighbours: hlast[j] = the state after the last
+ *                     segment, dtsum[j] = sum over the segments of seg_dtsum.  h0 / carry / hlast / dtsum may be NULL.  (N == 16)
+ *   the carries are then applied by cad_bimamba_scan_fixup with nseg / seg_carry set (seg_first = 1 when h0 was given).      */
 int cad_bc_transpose(const float* bc, float* bcT, int64_t njobs, int64_t N2, int64_t L, int64_t ldbc, void* stream);
-int cad_seg_carry(const float* seg_state, const float* seg_dtsum, const float* A2, const int32_t* pset_of_job, float* carry,
-                  int64_t njobs, int64_t nseg, int64_t E, void* stream);
+int cad_seg_carry(const float* seg_state, const float* seg_dtsum, const float* A2, const int32_t* pset_of_job, const float* h0,
+                  float* carry, float* hlast, float* dtsum, int64_t njobs, int64_t nseg, int64_t E, void* stream);
 
 /* ---- carry fix-up of a sequence-sharded scan: adds, in place, the contribution of the carry-in
  *      state h0 to an output that was produced by cad_bimamba_scan_fwd with a ZERO carry:
@@ -197,6 +199,7 @@ typedef struct {
    * segment's own token range (the split of cad_scan_fwd_args.nseg) with the carry  seg_carry[job, s]; h0 is ignored.      */
   int32_t nseg;
   const float* seg_carry;   /* (njobs, nseg, E, N) from cad_seg_carry */
+  int32_t seg_first;        /* 1: logical segment 0 is fixed up as well (its carry is the shard's own carry-in h0) */
 } cad_scan_fixup_args;
 int cad_bimamba_scan_fixup(const cad_scan_fixup_args* a, void* stream);
 

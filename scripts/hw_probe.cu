@@ -377,7 +377,7 @@ static int group_v20(int64_t L) {
     f.L = L; f.E = E; f.N = N; f.ldxz = L; f.ldd = L; f.ldbc = L; f.ldo = L;
     f.nseq = p.nseq; f.njobs = p.njobs; f.io_dtype = CAD_BF16; f.cutoff_log2 = -24.f; f.nseg = c.nseg; f.seg_carry = carry;
     auto pass_a = [&]() { int rc = cad_bimamba_scan_fwd(&a, nullptr); if (rc) say("D: v20 launch rc %d: %s", rc, cad_last_error()); return rc; };
-    auto compose = [&]() { return c.nseg > 1 ? cad_seg_carry(seg_state, seg_dtsum, p.A2, p.pset, carry, p.njobs, c.nseg, E, nullptr) : 0; };
+    auto compose = [&]() { return c.nseg > 1 ? cad_seg_carry(seg_state, seg_dtsum, p.A2, p.pset, nullptr, carry, nullptr, nullptr, p.njobs, c.nseg, E, nullptr) : 0; };
     auto fixup = [&]() { int rc = c.nseg > 1 ? cad_bimamba_scan_fixup(&f, nullptr) : 0; if (rc) say("D: fix-up rc %d: %s", rc, cad_last_error()); return rc; };
     CK(cudaMemset(p.out_var, 0xFF, (size_t)n_out * 2));
     if (pass_a() || compose() || fixup()) return 1;

@@ -169,7 +169,7 @@ extern "C" int emu_scan_fixup(const cad_scan_fixup_args* a, int G) {
   tmap.nblk = (a->L + 31) / 32;
   tmap.box_blocks = fx::kChunk / 32;
   tmap.box_rows = 16;
-  const int gx = (int)((a->E + G - 1) / G), gy = a->nseg > 1 ? a->njobs * (a->nseg - 1) : a->njobs;
+  const int gx = (int)((a->E + G - 1) / G), gy = a->nseg > 1 ? a->njobs * (a->nseg - (a->seg_first ? 0 : 1)) : a->njobs;
   const size_t sb = 1024 + (size_t)16 * fx::kChunk * 4 + (size_t)2 * fx::kMaxG * 16 * 4 + 16;
   for (int by = 0; by < gy; ++by)
     for (int bx = 0; bx < gx; ++bx) {

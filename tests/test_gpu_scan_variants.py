@@ -151,6 +151,34 @@ def test_v20_lane_per_channel_vs_boundary_restatement(L, rev, nseg):
 
 
 @unmeasured
+@pytest.mark.parametrize("nseg", [1, 4])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_v20_as_a_sequence_shard(rev, nseg):
+    """variant 20 behind the sharding hooks: conv halo in, zero-carry end state + sum dt out (composed from
+    the segments), then the shard's carry-in applied to every segment by ONE fix-up launch."""
+    from caduceus_b200 import functional as CF
+    L, E, dtype = 2300, 96, torch.bfloat16
+    spec = [(0, 0, rev), (0, 1, 1 - rev)]
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, 41)
+    bc = bc.to(dtype).float()
+    g = torch.Generator().manual_seed(2)
+    halo, h0 = torch.randn(2, E, 3, generator=g).to(dtype), torch.randn(2, E, 16, generator=g)
+    d = lambda t: t.to(DEV).contiguous()   # noqa: E731
+    packed, jobs = tuple(d(t) for t in (conv_w4, conv_b, dt_b, A2, Dk)), tuple(d(t) for t in tabs)
+    out, hl, ds, ctx = CF.scan_fwd(d(xz), d(delta), d(bc), packed, jobs, L, halo=d(halo), want_state=True, variant=20, nseg=nseg)
+    f = lambda t: t.float().numpy()   # noqa: E731
+    args = (f(xz), f(delta), f(bc), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk), [0, 0], [0, 1], [rev, 1 - rev], L)
+    zero = boundary_ref(*args, halo=f(halo), full=True)
+    assert np.allclose(hl.cpu().numpy(), zero[1], rtol=2e-3, atol=2e-3 * max(1.0, np.abs(zero[1]).max()))
+    assert np.allclose(ds.cpu().numpy(), zero[2], rtol=2e-3, atol=1e-3)
+    CF.scan_fixup(d(xz), d(delta), d(bc), out, packed, jobs, L, d(h0), seg_ctx=ctx)
+    ref = boundary_ref(*args, halo=f(halo), h0=f(h0))
+    got = out[..., :L].float().cpu().numpy()
+    err, bound = np.abs(got - ref), 1e-2 + 1.5e-2 * np.abs(ref)
+    assert np.isfinite(got).all() and (err <= bound).all(), (err.max(), (err - bound).max())
+
+
+@unmeasured
 def test_v20_helpers_transpose_and_carry_composition():
     from caduceus_b200 import _lib, functional as CF
     import ctypes as C
@@ -166,11 +194,15 @@ def test_v20_helpers_transpose_and_carry_composition():
     A2 = -(torch.rand(2, E, 16, generator=g) * 8).to(DEV)
     pset = torch.tensor([0, 1, 0], dtype=torch.int32, device=DEV)
     carry = torch.empty(njobs, nseg, E, 16, device=DEV)
-    _lib.check(lib.cad_seg_carry(p(st), p(ds), p(A2), p(pset), p(carry), njobs, nseg, E, CF._stream()), "cad_seg_carry")
-    h = torch.zeros(njobs, E, 16, device=DEV, dtype=torch.float64)
+    h0 = torch.randn(njobs, E, 16, generator=g).to(DEV)
+    hlast, dtsum = torch.empty(njobs, E, 16, device=DEV), torch.empty(njobs, E, device=DEV)
+    _lib.check(lib.cad_seg_carry(p(st), p(ds), p(A2), p(pset), p(h0), p(carry), p(hlast), p(dtsum), njobs, nseg, E,
+                                 CF._stream()), "cad_seg_carry")
+    h = h0.double()
     for s_ in range(nseg):
         assert torch.allclose(carry[:, s_].double(), h, rtol=1e-4, atol=1e-5), s_
         h = torch.exp2(A2[pset.long()].double() * ds[:, s_, :, None].double()) * h + st[:, s_].double()
+    assert torch.allclose(hlast.double(), h, rtol=1e-4, atol=1e-5) and torch.allclose(dtsum, ds.sum(1), rtol=1e-5)
 
 
 def test_v4_rejects_what_it_does_not_cover():

@@ -193,7 +193,7 @@ def test_argument_marshalling_and_validation_reach_the_library_without_a_gpu(mon
     with pytest.raises(RuntimeError, match="cad_bc_transpose failed"):          # variant 20: first launch of its pipeline
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=20, nseg=1)
     with pytest.raises(RuntimeError, match="inference only"):
-        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=20, want_state=True)
+        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=20, h0=torch.zeros(1, 64, 16))
     with pytest.raises(RuntimeError, match="delta_is_dt needs variant 9..12"):
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=3, delta_is_dt=True)
     with pytest.raises(RuntimeError, match="cad_bimamba_scan_fwd failed .*cuTensorMapEncodeTiled"):
