@@ -350,7 +350,9 @@ def run_b200(a):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
             if a.seqlen == 131072 and a.d_model == 256 and a.batch == 1 and not shard_seq:
-                traffic = tj[a.model + ("_v4" if scan_v4 else "")]["dram_bytes_per_launch"]
+                # measured traffic exists per kernel variant: no entry for the running variant -> null, not another kernel's number
+                v_run = 4 if scan_v4 else (CF.SCAN_VARIANT if (CF.SCAN_VARIANT and not train) else 3)
+                traffic = tj.get(a.model + ("" if v_run == 3 else f"_v{v_run}"), {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         plain = not train and not shard_seq           # the non-default variants cover the plain inference call
