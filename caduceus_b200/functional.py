@@ -4,7 +4,6 @@ PyTorch is plumbing here (device memory, streams, the dense cuBLAS projections);
 path is in csrc/*.cu.  Every function raises RuntimeError on non-CUDA tensors — there is no CPU fallback.
 """
 import ctypes as C
-import math
 import os
 
 import torch
