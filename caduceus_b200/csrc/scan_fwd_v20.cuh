@@ -147,8 +147,11 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
     }
     auto halo_at = [&](int64_t tau) -> float { return tau == -1 ? hal2 : (tau == -2 ? hal1 : (tau == -3 ? hal0 : 0.f)); };
     auto x_at = [&](int64_t t) -> float { return (t >= 0 && t < L) ? io<T>::to_f(xrow[t]) : halo_at(REV ? L - 1 - t : t); };
+    // conv window = the three x values that logically precede the FIRST PROCESSED token.  Reversed: that token is the last of
+    // the block's last 8-token group, which lies beyond t_hi - 1 when the sequence end is ragged (the masked tokens in between
+    // then push their own halo / zero values, so starting the window at t_hi would enter them twice)
     float w0, w1, w2;
-    if (REV) { w0 = x_at(t_hi + 2); w1 = x_at(t_hi + 1); w2 = x_at(t_hi); }
+    if (REV) { const int64_t tf = ((t_hi + GT - 1) / GT) * GT - 1; w0 = x_at(tf + 3); w1 = x_at(tf + 2); w2 = x_at(tf + 1); }
     else     { w0 = x_at(t_lo - 3); w1 = x_at(t_lo - 2); w2 = x_at(t_lo - 1); }
 
     // groups of 8 tokens [8 g, 8 g + 8), g in [g_lo, g_hi], walked in logical order (descending when reversed);

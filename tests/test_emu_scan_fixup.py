@@ -67,7 +67,7 @@ def test_emulated_v20_pipeline_pass_a_carry_fixup(emu, L, nseg, cutoff):   # noq
     _pipeline(emu, L, nseg, cutoff, shard=False)
 
 
-@pytest.mark.parametrize("L,nseg", [(5, 2), (700, 2), (1537, 3), (1100, 5)])
+@pytest.mark.parametrize("L,nseg", [(5, 2), (700, 2), (1537, 3), (1100, 5), (767, 3), (1022, 2)])   # 767, 1022: fewer than 3 masked tail tokens
 def test_emulated_v20_pipeline_as_a_sequence_shard(emu, L, nseg):   # noqa: F811
     """The same pipeline as ONE SHARD of a longer sequence: conv halo into the segment scans, the shard's
     carry-in h0 into the carry composition, every segment (the first included) fixed up in one launch; the composed end

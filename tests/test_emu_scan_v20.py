@@ -106,6 +106,31 @@ def test_emulated_v20_segments_compose_to_the_unsegmented_scan(emu, L, nseg):   
     _run(emu, L, E=40, spec=spec, dtype=torch.float16, W=2, seed=31 + nseg, nseg=nseg)
 
 
+@pytest.mark.parametrize("L", [6, 7, 767, 1022])
+def test_emulated_v20_halo_with_fewer_than_three_masked_tail_tokens(emu, L):   # noqa: F811
+    """Reversed job + conv halo + a ragged end with 1 or 2 masked tokens in the last 8-token group: the masked tokens carry
+    halo values themselves, so the initial conv window must start beyond them (regression: they were entered twice)."""
+    import ctypes as C2
+    xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, 8, [(0, 0, 1), (0, 1, 0)], torch.bfloat16, 3100 + L)
+    g = torch.Generator().manual_seed(L)
+    halo = torch.randn(2, 8, 3, generator=g).to(torch.bfloat16)
+    Lp = (L + CH - 1) // CH * CH
+    bcT = torch.zeros(2, Lp, 2 * N)
+    bcT[:, :L] = bc[..., :L].transpose(1, 2)
+    out = torch.full((2, 8, ld), float("nan")).to(torch.bfloat16)
+    p = lambda t: None if t is None else C2.c_void_p(t.data_ptr())   # noqa: E731
+    a = _lib.ScanFwdArgs(p(xz), p(delta), None, p(out), p(conv_w4), p(conv_b), p(dt_b), p(A2), p(Dk),
+                         p(tabs[0]), p(tabs[1]), p(tabs[2]), p(halo), None, None, None, None,
+                         L, 8, N, 4, ld, ld, ldbc, ld, xz.shape[0], 2, conv_w4.shape[0], _lib.CAD_BF16, 1, 0, 0, 20, None, 0, 0,
+                         p(bcT), 1, None, None)
+    assert emu.emu_scan_v20(C2.byref(a), 1) == 0
+    f = lambda t: t.float().numpy()   # noqa: E731
+    ref = boundary_ref(f(xz), f(delta), f(bc), f(conv_w4), f(conv_b), f(dt_b), f(A2), f(Dk), [0, 0], [0, 1], [1, 0], L, halo=f(halo))
+    got = out.float().numpy()[..., :L]
+    err, bound = np.abs(got - ref), 1e-4 + 1.5 * 2.0 ** -8 * np.abs(ref)
+    assert (err <= bound).all(), (err.max(), (err - bound).max())
+
+
 def test_emulated_v20_dt_precomputed_and_many_chunks(emu):   # noqa: F811
     _run(emu, 2300, E=64, spec=[(0, 0, 0), (0, 1, 1)], dtype=torch.bfloat16, W=1, seed=5, nseg=2, dt_ready=True)
 
