@@ -69,8 +69,9 @@ while time.time() - t0 < args.seconds:
             count["v4"] += 1
         else:
             shard, nseg = rng.random() < 0.5, rng.choice([2, 3, 4, 5, 7, 9])
-            cfg = ("v20 shard" if shard else "v20", L, nseg)
-            TF._pipeline(lib, L, nseg, rng.choice([-24.0, -40.0]), shard=shard)
+            E20, W20, var = rng.choice([8, 32, 40, 64, 70]), rng.choice([1, 2, 3]), rng.choice([20, 20, 21, 22, 23])
+            cfg = ("v20 shard" if shard else "v20", L, nseg, E20, W20, var)
+            TF._pipeline(lib, L, nseg, rng.choice([-24.0, -40.0]), shard=shard, E=E20, W=W20, variant=var)
             count["v20 shard" if shard else "v20"] += 1
     except AssertionError as exc:
         print("FAIL", cfg, str(exc)[:300], flush=True)

@@ -75,8 +75,8 @@ def test_emulated_v20_pipeline_as_a_sequence_shard(emu, L, nseg):   # noqa: F811
     _pipeline(emu, L, nseg, -24.0, shard=True)
 
 
-def _pipeline(emu, L, nseg, cutoff, shard):   # noqa: F811
-    E, W, dtype = 40, 2, torch.bfloat16
+def _pipeline(emu, L, nseg, cutoff, shard, E=40, W=2, variant=20):   # noqa: F811
+    dtype = torch.bfloat16
     spec = [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0)]
     prob = _problem(L, E, spec, dtype, 70 + L + nseg)
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = prob
@@ -94,7 +94,7 @@ def _pipeline(emu, L, nseg, cutoff, shard):   # noqa: F811
     seg_dtsum = torch.full((njobs, nseg, E), float("nan"))
     a = _lib.ScanFwdArgs(p(xz), p(delta), None, p(out), p(conv_w4), p(conv_b), p(dt_b), p(A2), p(Dk),
                          p(tabs[0]), p(tabs[1]), p(tabs[2]), p(halo), None, None, None, None,
-                         L, E, N, 4, ld, ld, ldbc, ld, xz.shape[0], njobs, conv_w4.shape[0], _io(dtype), W, 0, 0, 20, None, 0, 0,
+                         L, E, N, 4, ld, ld, ldbc, ld, xz.shape[0], njobs, conv_w4.shape[0], _io(dtype), W, 0, 0, variant, None, 0, 0,
                          p(bcT), nseg, p(seg_state), p(seg_dtsum))
     assert emu.emu_scan_v20(C.byref(a), W) == 0
     part = out[..., :L].float().numpy().copy()
