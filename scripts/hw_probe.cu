@@ -364,9 +364,11 @@ static int group_v20(int64_t L) {
   float tmin, tmean;
   if (time_launches([&]() { return cad_bc_transpose(p.bc, bcT, p.njobs, 2 * N, L, L, nullptr); }, 1, 4, &tmin, &tmean)) return 1;
   say("D: cad_bc_transpose (64 MiB in, 64 MiB out)  min %.3f ms mean %.3f ms", tmin, tmean);
-  struct Cfg { int nseg, W, variant; };
-  const Cfg cfgs[] = {{1, 8, 20}, {37, 8, 20}, {18, 8, 20}, {18, 4, 20}, {9, 4, 20}, {9, 2, 20}, {5, 2, 20}, {37, 4, 20}, {74, 4, 20},
-                      {37, 8, 21}, {37, 8, 22}, {37, 8, 23}, {18, 8, 22}};      // 21..23: exp2 of 1 / 2 / 3 state pairs on the FMA pipe
+  struct Cfg { int nseg, W, variant; float cutoff; };
+  const Cfg cfgs[] = {{1, 8, 20, -24.f}, {37, 8, 20, -24.f}, {18, 8, 20, -24.f}, {18, 4, 20, -24.f}, {9, 4, 20, -24.f}, {9, 2, 20, -24.f},
+                      {5, 2, 20, -24.f}, {37, 4, 20, -24.f}, {74, 4, 20, -24.f},
+                      {37, 8, 20, -40.f}, {37, 8, 20, -16.f},                  // how much of the fix-up is the cut-off's tail
+                      {37, 8, 21, -24.f}, {37, 8, 22, -24.f}, {37, 8, 23, -24.f}, {18, 8, 22, -24.f}};   // 21..23: exp2 of 1 / 2 / 3 state pairs on the FMA pipe
   for (const Cfg& c : cfgs) {
     cad_scan_fwd_args a = fwd_args(p, c.variant, false, p.out_var);
     a.bc = nullptr; a.bcT = bcT; a.nseg = c.nseg; a.seg_state = seg_state; a.seg_dtsum = seg_dtsum; a.channels_per_cta = c.W;
@@ -375,7 +377,7 @@ static int group_v20(int64_t L) {
     f.xz = p.xz; f.delta = p.delta; f.bc = p.bc; f.out = p.out_var; f.dt_b = p.dt_b; f.A2 = p.A2;
     f.seq_of_job = p.seq; f.pset_of_job = p.pset; f.rev_of_job = p.rev;
     f.L = L; f.E = E; f.N = N; f.ldxz = L; f.ldd = L; f.ldbc = L; f.ldo = L;
-    f.nseq = p.nseq; f.njobs = p.njobs; f.io_dtype = CAD_BF16; f.cutoff_log2 = -24.f; f.nseg = c.nseg; f.seg_carry = carry;
+    f.nseq = p.nseq; f.njobs = p.njobs; f.io_dtype = CAD_BF16; f.cutoff_log2 = c.cutoff; f.nseg = c.nseg; f.seg_carry = carry;
     auto pass_a = [&]() { int rc = cad_bimamba_scan_fwd(&a, nullptr); if (rc) say("D: v20 launch rc %d: %s", rc, cad_last_error()); return rc; };
     auto compose = [&]() { return c.nseg > 1 ? cad_seg_carry(seg_state, seg_dtsum, p.A2, p.pset, nullptr, carry, nullptr, nullptr, p.njobs, c.nseg, E, nullptr) : 0; };
     auto fixup = [&]() { int rc = c.nseg > 1 ? cad_bimamba_scan_fixup(&f, nullptr) : 0; if (rc) say("D: fix-up rc %d: %s", rc, cad_last_error()); return rc; };
@@ -394,8 +396,8 @@ static int group_v20(int64_t L) {
       if (time_launches(fixup, 1, it, &tf, &tfm)) return 1;
     }
     if (time_launches([&]() { return pass_a() || compose() || fixup(); }, 1, it, &tall, &tallm)) return 1;
-    say("D: v%d nseg %2d W %d  max|diff vs v3| %.3e (max|ref| %.3e, non-finite %u)   pass A %.3f  carry %.3f  fix-up %.3f  "
-        "whole pipeline min %.3f mean %.3f ms", c.variant, c.nseg, c.W, m.maxdiff, m.maxref, m.bad, ta, tc, tf, tall, tallm);
+    say("D: v%d nseg %2d W %d cut %.0f  max|diff vs v3| %.3e (max|ref| %.3e, non-finite %u)   pass A %.3f  carry %.3f  fix-up %.3f  "
+        "whole pipeline min %.3f mean %.3f ms", c.variant, c.nseg, c.W, c.cutoff, m.maxdiff, m.maxref, m.bad, ta, tc, tf, tall, tallm);
   }
   return 0;
 }
