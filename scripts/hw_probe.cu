@@ -352,7 +352,7 @@ static int group_v20(int64_t L) {
   CK(cudaFree(0));
   Problem p;
   if (make_problem(p, L, 4)) return 1;
-  const int64_t E = p.E, N = p.N, n_out = (int64_t)p.njobs * E * L, Lp = (L + 255) / 256 * 256;
+  const int64_t E = p.E, N = p.N, Lp = (L + 255) / 256 * 256;
   cad_scan_fwd_args r = fwd_args(p, 3, false, p.out_ref);
   if (cad_bimamba_scan_fwd(&r, nullptr)) { say("D: v3 reference failed: %s", cad_last_error()); return 1; }
   float *bcT, *seg_state, *seg_dtsum, *carry;
@@ -364,12 +364,16 @@ static int group_v20(int64_t L) {
   float tmin, tmean;
   if (time_launches([&]() { return cad_bc_transpose(p.bc, bcT, p.njobs, 2 * N, L, L, nullptr); }, 1, 4, &tmin, &tmean)) return 1;
   say("D: cad_bc_transpose (64 MiB in, 64 MiB out)  min %.3f ms mean %.3f ms", tmin, tmean);
-  struct Cfg { int nseg, W, variant; float cutoff; };
+  struct Cfg { int nseg, W, variant; float cutoff; int njobs; };      // njobs 4 = Caduceus-PS launch, 2 = Caduceus-Ph (the first two jobs)
   const Cfg cfgs[] = {{1, 8, 20, -24.f}, {37, 8, 20, -24.f}, {18, 8, 20, -24.f}, {18, 4, 20, -24.f}, {9, 4, 20, -24.f}, {9, 2, 20, -24.f},
                       {5, 2, 20, -24.f}, {37, 4, 20, -24.f}, {74, 4, 20, -24.f},
                       {37, 8, 20, -40.f}, {37, 8, 20, -16.f},                  // how much of the fix-up is the cut-off's tail
-                      {37, 8, 21, -24.f}, {37, 8, 22, -24.f}, {37, 8, 23, -24.f}, {18, 8, 22, -24.f}};   // 21..23: exp2 of 1 / 2 / 3 state pairs on the FMA pipe
+                      {37, 8, 21, -24.f}, {37, 8, 22, -24.f}, {37, 8, 23, -24.f}, {18, 8, 22, -24.f},   // 21..23: exp2 of 1 / 2 / 3 state pairs on the FMA pipe
+                      {37, 4, 20, -24.f, 2}, {18, 4, 20, -24.f, 2}, {18, 2, 20, -24.f, 2}, {37, 4, 22, -24.f, 2}};   // Caduceus-Ph (variant 3: 1.54 ms)
   for (const Cfg& c : cfgs) {
+    p.njobs = c.njobs ? c.njobs : 4;
+    p.nseq = p.njobs / 2;
+    const int64_t n_out = (int64_t)p.njobs * E * L;
     cad_scan_fwd_args a = fwd_args(p, c.variant, false, p.out_var);
     a.bc = nullptr; a.bcT = bcT; a.nseg = c.nseg; a.seg_state = seg_state; a.seg_dtsum = seg_dtsum; a.channels_per_cta = c.W;
     cad_scan_fixup_args f;
@@ -396,8 +400,8 @@ static int group_v20(int64_t L) {
       if (time_launches(fixup, 1, it, &tf, &tfm)) return 1;
     }
     if (time_launches([&]() { return pass_a() || compose() || fixup(); }, 1, it, &tall, &tallm)) return 1;
-    say("D: v%d nseg %2d W %d cut %.0f  max|diff vs v3| %.3e (max|ref| %.3e, non-finite %u)   pass A %.3f  carry %.3f  fix-up %.3f  "
-        "whole pipeline min %.3f mean %.3f ms", c.variant, c.nseg, c.W, c.cutoff, m.maxdiff, m.maxref, m.bad, ta, tc, tf, tall, tallm);
+    say("D: %s v%d nseg %2d W %d cut %.0f  max|diff vs v3| %.3e (max|ref| %.3e, non-finite %u)   pass A %.3f  carry %.3f  fix-up %.3f  "
+        "whole pipeline min %.3f mean %.3f ms", p.njobs == 4 ? "PS" : "Ph", c.variant, c.nseg, c.W, c.cutoff, m.maxdiff, m.maxref, m.bad, ta, tc, tf, tall, tallm);
   }
   return 0;
 }
