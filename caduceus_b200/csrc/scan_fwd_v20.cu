@@ -29,6 +29,7 @@ int launch_scan_v20(const cad_scan_fwd_args& a, cudaStream_t stream) {
               "sum dt come from cad_seg_carry on the segment outputs, not from this launch)");
   CAD_REQUIRE(a.bcT && aligned16(a.bcT), "cad_bimamba_scan_fwd: variant 20 needs bcT (cad_bc_transpose), 16-byte aligned");
   CAD_REQUIRE(nseg <= 4096, "cad_bimamba_scan_fwd: nseg out of range");
+  CAD_REQUIRE(a.L < (int64_t(1) << 31) - 4096, "cad_bimamba_scan_fwd: variant 20 keeps token-group counters in 32 bits");
   CAD_REQUIRE(nseg == 1 || (a.seg_state && a.seg_dtsum), "cad_bimamba_scan_fwd: nseg > 1 needs seg_state and seg_dtsum");
   CAD_REQUIRE(!a.seg_state || (aligned16(a.seg_state) && a.seg_dtsum), "cad_bimamba_scan_fwd: seg_state must be 16-byte "
               "aligned and come with seg_dtsum");
