@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcaduceus_b200.so")
 
 CAD_F32, CAD_F16, CAD_BF16 = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -116,6 +116,11 @@ class ConvFwdArgs(C.Structure):
                 ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32)]
 
 
+class PeerCtx(C.Structure):
+    _fields_ = [("peer_ws", _p), ("rank", _i32), ("world", _i32),
+                ("nseq_max", _i64), ("njobs_max", _i64), ("E", _i64), ("N", _i64)]
+
+
 # every symbol include/caduceus_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "cad_version": (C.c_int, []),
@@ -136,6 +141,9 @@ SYMBOLS = {
     "cad_bimamba_scan_adjoint": (C.c_int, [C.POINTER(ScanAdjointArgs), _p]),
     "cad_bc_transpose": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "cad_seg_carry": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
+    "cad_peer_ws_bytes": (_i64, [_i32, _i64, _i64, _i64, _i64]),
+    "cad_peer_halo_exchange": (C.c_int, [C.POINTER(PeerCtx), _p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _p]),
+    "cad_peer_carry_exchange": (C.c_int, [C.POINTER(PeerCtx), _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "cad_hg38_batch_fwd": (C.c_int, [C.POINTER(Hg38BatchArgs), _p]),
     "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),
 }

@@ -40,6 +40,12 @@ CAD_DEV void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, u
 }
 template <int N> CAD_DEV void cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 CAD_DEV void stg128f(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+CAD_DEV uint32_t lds16u(uint32_t addr) {               // one 16-bit element of a staged row (zero-extended)
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+CAD_DEV void sts16u(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory"); }
 CAD_DEV uint32_t f2u(float f) { return __float_as_uint(f); }
 CAD_DEV float u2f(uint32_t u) { return __uint_as_float(u); }
 #endif
@@ -129,7 +135,7 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
 
   if (t_lo < t_hi) {                                         // CTA-uniform
     const T* __restrict__ xrow = static_cast<const T*>(a.xz) + ((int64_t)seq * 2 * E + chc) * a.ldxz;
-    const T* __restrict__ zrow = xrow + E * a.ldxz;
+    const int64_t zoff = E * a.ldxz;                            // z row of the same channel (uniform offset)
     const T* __restrict__ drow = static_cast<const T*>(a.delta) + ((int64_t)job * E + chc) * a.ldd;
     T* __restrict__ orow = static_cast<T*>(a.out) + ((int64_t)job * E + chc) * a.ldo;
     const int64_t pc = (int64_t)pset * E + chc;
@@ -139,13 +145,10 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) A2p[p] = make_float2(a.A2[pc * NST + 2 * p], a.A2[pc * NST + 2 * p + 1]);
 
-    // x outside the sequence: the conv halo (x at logical times -3, -2, -1: sequence sharding) before logical time 0, else zero
-    float hal0 = 0.f, hal1 = 0.f, hal2 = 0.f;
-    if (a.halo) {
-      const T* hp = static_cast<const T*>(a.halo) + ((int64_t)job * E + chc) * 3;
-      hal0 = io<T>::to_f(hp[0]); hal1 = io<T>::to_f(hp[1]); hal2 = io<T>::to_f(hp[2]);
-    }
-    auto halo_at = [&](int64_t tau) -> float { return tau == -1 ? hal2 : (tau == -2 ? hal1 : (tau == -3 ? hal0 : 0.f)); };
+    // x outside the sequence: the conv halo (x at logical times -3, -2, -1: sequence sharding) before logical time 0, else zero.
+    // Read from memory where needed (segment start, masked tail tokens): three registers less in the hot loop.
+    const T* hp = a.halo ? static_cast<const T*>(a.halo) + ((int64_t)job * E + chc) * 3 : nullptr;
+    auto halo_at = [&](int64_t tau) -> float { return (hp && tau >= -3 && tau <= -1) ? io<T>::to_f(hp[tau + 3]) : 0.f; };
     auto x_at = [&](int64_t t) -> float { return (t >= 0 && t < L) ? io<T>::to_f(xrow[t]) : halo_at(REV ? L - 1 - t : t); };
     // conv window = the three x values that logically precede the FIRST PROCESSED token.  Reversed: that token is the last of
     // the block's last 8-token group, which lies beyond t_hi - 1 when the sequence end is ragged (the masked tokens in between
@@ -159,18 +162,16 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
     const int g_lo = (int)(t_lo / GT), g_hi = (int)((t_hi + GT - 1) / GT) - 1, ng = g_hi - g_lo + 1;
     constexpr int gstep = REV ? -1 : 1;
     const uint32_t ring = sm.ring + (uint32_t)warp * (kStages * kStageBytes) + (uint32_t)lane * 16;
-    int q_stage = 0, g_stage = REV ? g_hi : g_lo;
-    auto stage_next = [&]() {                                 // every call commits (uniform group counting)
-      if (q_stage < ng) {
-        const int64_t t = (int64_t)g_stage * GT;
-        const uint32_t s = ring + (uint32_t)(q_stage & (kStages - 1)) * kStageBytes;
-        cp_async16s(s, xrow + t);
-        cp_async16s(s + 512, drow + t);
-        cp_async16s(s + 1024, zrow + t);
+    // group q + kAhead is staged while group q is consumed; every call commits (uniform cp.async group counting)
+    auto stage = [&](int qs, int gs) {
+      if (qs < ng) {
+        const T* src = xrow + (int64_t)gs * GT;
+        const uint32_t s = ring + (uint32_t)(qs & (kStages - 1)) * kStageBytes;
+        cp_async16s(s, src);
+        cp_async16s(s + 512, drow + (int64_t)gs * GT);
+        cp_async16s(s + 1024, src + zoff);
       }
       cp_commit();
-      ++q_stage;
-      g_stage += gstep;
     };
     // chunks of this block, logical order
     const int c_lo = (int)(t_lo / CH), c_hi = (int)((t_hi + CH - 1) / CH) - 1, nc = c_hi - c_lo + 1;
@@ -179,26 +180,34 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
     auto issue_chunk = [&](int qc, int buf) {
       const int c = REV ? c_hi - qc : c_lo + qc;
       mbar_expect_tx(&sm.bar[buf], kTileBytes);
-      bulk_load_1d(sm.tile[buf], bct + (int64_t)c * CH * 2 * NST, kTileBytes, &sm.bar[buf]);
+      bulk_load_1d(sm.tile[0] + (uint32_t)buf * kTileBytes, bct + (int64_t)c * CH * 2 * NST, kTileBytes, &sm.bar[buf]);
     };
     if (CAD_TID == 0) {
       issue_chunk(0, 0);
       if (nc > 1) issue_chunk(1, 1);
     }
 #pragma unroll
-    for (int k2 = 0; k2 < kAhead; ++k2) stage_next();
+    for (int k2 = 0; k2 < kAhead; ++k2) stage(k2, (REV ? g_hi : g_lo) + gstep * k2);
 
     // one group of 8 tokens: conv + SiLU, dt, the 16 state recurrences as 8 packed pairs, gate, store
     auto group = [&](auto tail_tag, int g, uint32_t stage_s, uint32_t trow) {
       constexpr bool TAIL = decltype(tail_tag)::value;        // the last physical group of the sequence: tokens >= L masked
-      const uint4 xq = lds128u(stage_s), dq = lds128u(stage_s + 512), zq = lds128u(stage_s + 1024);
-      const T* xe = reinterpret_cast<const T*>(&xq);
-      const T* ze = reinterpret_cast<const T*>(&zq);
+      // dt_raw of the 8 tokens at once (8 independent softplus chains); x and z are re-read per token as 16-bit elements from the
+      // staged rows instead of being held in 8 registers across the group (the kernel sits at the 128-register cap of two CTAs per
+      // SM: holding them spilled loop counters, 1.56 instead of 1.36 ms per Caduceus-PS launch).  Lanes 8 apart share a bank, so such
+      // a read is 4 wavefronts; reading token PAIRS as words halves that but measured slower (1.42 ms: longer chain per token).
+      const uint4 dq = lds128u(stage_s + 512);
       const T* de = reinterpret_cast<const T*>(&dq);
       const __half* dh = reinterpret_cast<const __half*>(&dq);
+      auto el16 = [](uint32_t bits) -> float {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) return u2f(bits << 16);
+        else return __half2float(__ushort_as_half((unsigned short)bits));
+      };
       const int64_t t0 = (int64_t)g * GT;
-      uint4 oq;
-      T* oe = reinterpret_cast<T*>(&oq);
+      auto to16 = [](float v) -> uint32_t {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+        else return (uint32_t)__half_as_ushort(__float2half_rn(v));
+      };
       float dv[GT];                                            // dt of the group's tokens (physical order)
       if (a.delta_is_dt) {                                     // launch-uniform: conv_xproj already applied the softplus
 #pragma unroll
@@ -212,7 +221,7 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
         const int pi = REV ? GT - 1 - i : i;                  // physical position inside the group
         const bool masked = TAIL && (t0 + pi >= L);
         // a masked token of a reversed job lies logically BEFORE the sequence: it feeds the conv window with the halo
-        const float xv = masked ? (REV ? halo_at(L - 1 - (t0 + pi)) : 0.f) : io<T>::to_f(xe[pi]);
+        const float xv = masked ? (REV ? halo_at(L - 1 - (t0 + pi)) : 0.f) : el16(lds16u(stage_s + 2 * pi));
         const float cv = cb + cw0 * w0 + cw1 * w1 + cw2 * w2 + cw3 * xv;
         w0 = w1; w1 = w2; w2 = xv;
         const float u = silu_io<T>(cv);
@@ -232,11 +241,15 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
           yb = fma2(make_float2(cq.z, cq.w), h2[2 * p4 + 1], yb);
         }
         const float y = fmaf(Dk, u, (ya.x + ya.y) + (yb.x + yb.y));
-        oe[pi] = io<T>::from_f(y * silu_io<T>(io<T>::to_f(ze[pi])));
+        // the gated output replaces z in this lane's own 16 bytes of the stage (no output registers held across the group);
+        // one LDS.128 + STG.128 per group below
+        sts16u(stage_s + 1024 + 2 * pi, to16(y * silu_io<T>(el16(lds16u(stage_s + 1024 + 2 * pi)))));
       }
       if (active) {
+        const uint4 oq = lds128u(stage_s + 1024);
         if (!TAIL) stg128(orow + t0, oq);
         else {
+          const T* oe = reinterpret_cast<const T*>(&oq);
 #pragma unroll
           for (int i = 0; i < GT; ++i)
             if (t0 + i < L) orow[t0 + i] = oe[i];
@@ -244,24 +257,25 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
       }
     };
 
-    uint32_t par0 = 0, par1 = 0;
+    const int g_tail = (L % GT) ? (int)(L / GT) : -1;           // the one group with masked tokens (ragged sequence end)
+    uint32_t par = 0;                                          // bit b: parity to wait for on chunk buffer b
     int q = 0, g = REV ? g_hi : g_lo;                         // logical group counter, physical group
 #pragma unroll 1
     for (int qc = 0; qc < nc; ++qc) {
       const int buf = qc & 1;
       const int c = REV ? c_hi - qc : c_lo + qc;
-      mbar_wait_wd(&sm.bar[buf], buf ? par1 : par0);
-      if (buf) par1 ^= 1; else par0 ^= 1;
-      const uint32_t tile_s = sm.tile[buf];
+      mbar_wait_wd(&sm.bar[buf], (par >> buf) & 1u);
+      par ^= 1u << buf;
+      const uint32_t tile_s = sm.tile[0] + (uint32_t)buf * kTileBytes;
       // groups of this chunk that belong to the block
       const int gc_lo = c * GPC > g_lo ? c * GPC : g_lo, gc_hi = (c * GPC + GPC - 1) < g_hi ? (c * GPC + GPC - 1) : g_hi;
 #pragma unroll 1
       for (int gi = gc_hi - gc_lo; gi >= 0; --gi, ++q, g += gstep) {
-        stage_next();
+        stage(q + kAhead, g + gstep * kAhead);
         cp_wait_group<kAhead>();
         const uint32_t stage_s = ring + (uint32_t)(q & (kStages - 1)) * kStageBytes;
         const uint32_t trow = tile_s + (uint32_t)(g * GT - c * CH) * (2 * NST * 4);
-        if ((int64_t)g * GT + GT > L) group(std::true_type{}, g, stage_s, trow);
+        if (g == g_tail) group(std::true_type{}, g, stage_s, trow);
         else group(std::false_type{}, g, stage_s, trow);
       }
       // release the chunk buffer; the LAST warp to arrive requests chunk qc + 2 into it

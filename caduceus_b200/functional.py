@@ -372,13 +372,14 @@ def default_nseg(njobs, E, L, warps_per_cta=8):
     return max(1, min(want, L // 2048))
 
 
-def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=-24.0, bcT=None,
+def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_per_cta=0, cutoff_log2=None, bcT=None,
                        want_state=False):
     """Scan variant 20 (lane = channel, csrc/scan_fwd_v20.cuh): token-major copy of B / C, every segment scanned from a zero
     state, carries composed (cad_seg_carry) and added in place by the segment mode of the fix-up kernel.  `a` is the
     marshalled argument block of scan_fwd (reused so that the two paths cannot drift apart).  cutoff_log2: a carry term is
-    dropped once its decay factor is below 2^cutoff — 2^-24 is 4 decimal orders under the ulp of the 16-bit outputs this
-    variant is restricted to (the multi-GPU path keeps 2^-40 because it also serves fp32 I/O).
+    dropped once its decay factor is below 2^cutoff; default 2^-16 for bf16 and 2^-20 for fp16 outputs — with all 16 states of a
+    channel at the threshold and |C h0| as large as the output itself that is 1/16 (1/32) of an output ulp (the multi-GPU path
+    keeps 2^-40 because it also serves fp32 I/O).
     Returns (out, hlast, dtsum, seg_ctx).  want_state (a sequence SHARD): the local carries are NOT applied
     here; hlast / dtsum are the shard's zero-carry end state and sum dt for the all_gather, and seg_ctx goes to
     scan_fixup(..., h0, seg_ctx=seg_ctx), which applies the shard's carry-in and the local carries in ONE pass."""
@@ -387,6 +388,8 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     conv_w4, conv_b, dt_b, A2, Dk = packed
     njobs, twoN, ldbc = bc.shape
     E, N, dev = a.E, twoN // 2, xz.device
+    if cutoff_log2 is None:
+        cutoff_log2 = -16.0 if xz.dtype == torch.bfloat16 else -20.0
     # warps (32 channels each) per CTA: fewer when there are few jobs, so that about 37 segments per job fill two CTAs per SM
     W = warps_per_cta if warps_per_cta > 0 else min(8 if njobs >= 4 else 4 if njobs >= 2 else 2, (E + 31) // 32)
     nseg = default_nseg(njobs, E, L, W) if nseg is None else int(nseg)
@@ -472,6 +475,42 @@ def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, chann
     _lib.check(lib.cad_bimamba_scan_fixup(C.byref(a), _stream()), "cad_bimamba_scan_fixup")
     _launched()
     return out
+
+
+# =====================================================================================================
+# sequence sharding over NVLink peer memory (csrc/peer_exchange.cu): no library collective on the data path
+# =====================================================================================================
+def peer_ws_bytes(world, nseq_max, njobs_max, E, N):
+    n = _lib.load().cad_peer_ws_bytes(world, nseq_max, njobs_max, E, N)
+    if n <= 0:
+        raise RuntimeError("cad_peer_ws_bytes: bad geometry")
+    return int(n)
+
+
+def peer_halo_exchange(pctx, xz, L, jobs):
+    """Conv halo of a sequence shard through the peers' memory: halo (njobs, E, 3) in xz's dtype.  pctx: _lib.PeerCtx."""
+    lib = _lib.load()
+    seq, _, rev = jobs
+    nseq, twoE, ldxz = xz.shape
+    njobs = seq.numel()
+    halo = torch.empty(njobs, twoE // 2, 3, device=xz.device, dtype=xz.dtype)
+    _lib.check(lib.cad_peer_halo_exchange(C.byref(pctx), _ptr(xz), ldxz, L, nseq, njobs, _ptr(seq), _ptr(rev), _ptr(halo),
+                                          _dt(xz), _stream()), "cad_peer_halo_exchange")
+    _launched()
+    return halo
+
+
+def peer_carry_exchange(pctx, hlast, dtsum, A2, jobs, want_dtsum_all=False):
+    """Boundary states through the peers' memory + carry composition: h0 (njobs, E, N) [, dtsum_all (world, njobs, E)]."""
+    lib = _lib.load()
+    _, pset, rev = jobs
+    njobs, E, N = hlast.shape
+    h0 = torch.empty_like(hlast)
+    dt_all = torch.empty(pctx.world, njobs, E, device=hlast.device, dtype=torch.float32) if want_dtsum_all else None
+    _lib.check(lib.cad_peer_carry_exchange(C.byref(pctx), _ptr(hlast.contiguous()), _ptr(dtsum.contiguous()), _ptr(A2), _ptr(pset),
+                                           _ptr(rev), njobs, _ptr(h0), _ptr(dt_all), _stream()), "cad_peer_carry_exchange")
+    _launched(2)
+    return (h0, dt_all) if want_dtsum_all else h0
 
 
 def scan_adjoint(xz, delta, bc, dout, packed, jobs, L, cutoff_log2=-40.0, channels_per_cta=0):

@@ -253,7 +253,13 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
     # ---- conv + SiLU, x_proj GEMM ----------------------------------------------------------------------
     sharded = shard is not None and shard.world > 1
     halo = None
-    if sharded:      # the 3 conv samples that logically precede this shard (one tiny all_gather)
+    peer = shard.peer if sharded else None
+    if peer is not None and not peer.covers(xz.shape[0], jobs[0].numel(), E, N):
+        raise RuntimeError(f"PeerExchange workspace {peer.geometry} does not cover this call "
+                           f"(nseq {xz.shape[0]}, njobs {jobs[0].numel()}, E {E}, N {N})")
+    if peer is not None:      # pushed into the neighbours' memory over NVLink, no collective (csrc/peer_exchange.cu)
+        halo = CF.peer_halo_exchange(peer.ctx, xz, L, jobs)
+    elif sharded:      # the 3 conv samples that logically precede this shard (one tiny all_gather)
         halo = seqshard.gather_halo(xz[:, :E, :], L, jobs[0], jobs[2], shard).to(act)
     if CF.conv_xproj_supported(xz, N, m0.dt_rank) and not _FORCE_UNFUSED_XPROJ:
         # one tensor-core kernel: conv+SiLU -> x_proj -> dt_proj; u never touches HBM
@@ -288,7 +294,10 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
         # add its decaying contribution in place (seqshard.py, csrc/scan_fixup.cu).  Ranks never wait for each other.
         # (with scan variant 20 the shard is itself cut into segments: seg_ctx carries their end states to the fix-up)
         yg, hl, ds, seg_ctx = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True, bc16=bc16)
-        h0 = seqshard.gather_carry(hl, ds, packed[3], jobs[1], jobs[2], shard)
+        if peer is not None:
+            h0 = CF.peer_carry_exchange(peer.ctx, hl, ds, packed[3], jobs)
+        else:
+            h0 = seqshard.gather_carry(hl, ds, packed[3], jobs[1], jobs[2], shard)
         CF.scan_fixup(xz, delta, bc, yg, packed, jobs, L, h0, seg_ctx=seg_ctx if isinstance(seg_ctx, dict) else None)
     del xz
 

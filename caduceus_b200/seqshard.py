@@ -26,36 +26,82 @@ per-shard adjoints once and runs the ordinary backward kernel with (h0, dhlast);
 over the ranks with `all_reduce_grads`.
 """
 import contextlib
+import threading
 
 import torch
 import torch.distributed as dist
 
-_CTX = None
+_TLS = threading.local()        # the active ShardContext is per THREAD (several virtual ranks may live in one test process)
 
 
 class ShardContext:
-    def __init__(self, group=None):
+    def __init__(self, group=None, peer=None):
         self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group) if peer is None else peer.rank
+        self.world = dist.get_world_size(group) if peer is None else peer.world
         # gloo (CPU tests, or several ranks sharing one GPU in CI) moves CUDA tensors through host memory; the
         # production backend is NCCL, which takes the device buffers as they are
-        self.host_staged = dist.get_backend(group) == "gloo"
+        self.host_staged = peer is None and dist.get_backend(group) == "gloo"
+        # PeerExchange: the forward's two exchanges go through the peers' memory (csrc/peer_exchange.cu) instead of a collective
+        self.peer = peer
+
+
+class PeerExchange:
+    """Symmetric workspace + peer address table for csrc/peer_exchange.cu (inference forward of a sequence-sharded model).
+
+    `PeerExchange.create(group, ...)` allocates the workspace with torch's symmetric memory (CUDA VMM handles exchanged over the
+    process group's store; every rank of one NVLink / NVSwitch box maps every peer's buffer), zero-fills it and barriers once.
+    `PeerExchange.from_buffers(rank, buffers, ...)` builds the same object from explicit device buffers — used by the tests to
+    run several virtual ranks inside one process on one GPU.  The kernels only need the table of base addresses."""
+
+    def __init__(self, rank, world, ptrs, device, nseq_max, njobs_max, E, N, keep=()):
+        from . import _lib
+        self.rank, self.world = int(rank), int(world)
+        self.table = torch.tensor([int(p) for p in ptrs], dtype=torch.int64, device=device)      # uint64 addresses
+        self.ctx = _lib.PeerCtx(self.table.data_ptr(), self.rank, self.world, nseq_max, njobs_max, E, N)
+        self.geometry = (nseq_max, njobs_max, E, N)
+        self._keep = keep            # whatever owns the memory (symmetric-memory handle / buffers)
+
+    @classmethod
+    def create(cls, group=None, *, nseq_max, njobs_max, E, N, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import functional as CF
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        nbytes = CF.peer_ws_bytes(world, nseq_max, njobs_max, E, N)
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        hdl = symm_mem.rendezvous(buf, group)
+        buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                       # nobody pushes before every workspace is zeroed
+        return cls(rank, world, list(hdl.buffer_ptrs), device, nseq_max, njobs_max, E, N, keep=(buf, hdl))
+
+    @classmethod
+    def from_buffers(cls, rank, buffers, *, nseq_max, njobs_max, E, N):
+        return cls(rank, len(buffers), [b.data_ptr() for b in buffers], buffers[0].device, nseq_max, njobs_max, E, N,
+                   keep=tuple(buffers))
+
+    def covers(self, nseq, njobs, E, N):
+        g = self.geometry
+        return nseq <= g[0] and njobs <= g[1] and E == g[2] and N == g[3]
 
 
 def current():
-    return _CTX
+    return getattr(_TLS, "ctx", None)
 
 
 @contextlib.contextmanager
-def sequence_parallel(group=None):
-    """Treat the sequence axis of every BiMamba call inside as sharded over `group` (default: WORLD)."""
-    global _CTX
-    prev, _CTX = _CTX, ShardContext(group)
+def sequence_parallel(group=None, peer=None):
+    """Treat the sequence axis of every BiMamba call inside as sharded over `group` (default: WORLD).
+    peer: a PeerExchange — the inference forward then exchanges halo and boundary states through the peers' memory
+    (no collective, CUDA-graph capturable); training and fp32 paths keep the NCCL exchange."""
+    prev = current()
+    _TLS.ctx = ShardContext(group, peer)
     try:
-        yield _CTX
+        yield _TLS.ctx
     finally:
-        _CTX = prev
+        _TLS.ctx = prev
 
 
 def _all_gather(t, ctx):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CAD_ABI_VERSION 3
+#define CAD_ABI_VERSION 4
 
 typedef enum { CAD_F32 = 0, CAD_F16 = 1, CAD_BF16 = 2 } cad_dtype;
 
@@ -202,6 +202,33 @@ typedef struct {
   int32_t seg_first;        /* 1: logical segment 0 is fixed up as well (its carry is the shard's own carry-in h0) */
 } cad_scan_fixup_args;
 int cad_bimamba_scan_fixup(const cad_scan_fixup_args* a, void* stream);
+
+/* ---- sequence sharding over the GPUs of one NVLink / NVSwitch box: the two per-layer exchanges of the sharded BiMamba call done by
+ *      kernels that store straight into the PEERS' memory (no library collective on the data path, no host round trip, capturable
+ *      in a CUDA graph).  This is the north_star's "exchange of the d_state boundary hidden state per layer over NVLink", in the
+ *      non-serial form of SURVEY.md §8e: every rank scans from zero, all boundary states are exchanged ONCE, each rank composes
+ *      its own carry.  The reference has no counterpart (it scales by DDP only, ref:train.py:629-639).
+ *
+ *      Every rank allocates a workspace of cad_peer_ws_bytes(...) bytes, zero-filled once, that all peers can address (CUDA IPC /
+ *      torch symmetric memory); peer_ws[r] is rank r's workspace as mapped into THIS process.  All ranks must issue the same
+ *      sequence of cad_peer_* calls.  A peer that never arrives makes the waiting kernel trap after 10 s (the launch fails).      */
+typedef struct {
+  const void* peer_ws;      /* DEVICE array of `world` uint64 base addresses */
+  int32_t rank, world;      /* world <= 16 */
+  int64_t nseq_max, njobs_max, E, N;   /* workspace geometry: the same values on every rank */
+} cad_peer_ctx;
+int64_t cad_peer_ws_bytes(int32_t world, int64_t nseq_max, int64_t njobs_max, int64_t E, int64_t N);
+/* conv halo: pushes the first / last three x samples of every sequence of this shard (xz rows [0, E), shard length L >= 3) to the
+ * left / right neighbour, waits for theirs and writes halo (njobs, E, 3) in the io dtype: the three samples that logically precede
+ * the shard for every job (zeros at the ends of the full sequence) — the `halo` argument of the conv / scan entry points.        */
+int cad_peer_halo_exchange(const cad_peer_ctx* ctx, const void* xz, int64_t ldxz, int64_t L, int32_t nseq, int32_t njobs,
+                           const int32_t* seq_of_job, const int32_t* rev_of_job, void* halo, int32_t io_dtype, void* stream);
+/* boundary state: pushes (hlast (njobs, E, N), dtsum (njobs, E)) of this shard's zero-carry scan to every rank, waits for all of
+ * them and composes this rank's carry-in  h0 (njobs, E, N):  h <- exp2(A2 * dtsum_r) * h + hlast_r  over the logical predecessors r.
+ * dtsum_all (world, njobs, E) optional (NULL): every rank's sum dt (the sharded backward composes adjoint carries with it).      */
+int cad_peer_carry_exchange(const cad_peer_ctx* ctx, const float* hlast, const float* dtsum, const float* A2,
+                            const int32_t* pset_of_job, const int32_t* rev_of_job, int32_t njobs, float* h0, float* dtsum_all,
+                            void* stream);
 
 /* ---- adjoint of the carry (sequence-sharded TRAINING, SURVEY.md §8e "Backward"): the gradient w.r.t. a shard's
  *      carry-in state produced by the shard's own tokens (adjoint carry-in taken as zero),

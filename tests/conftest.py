@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# the virtual-rank tests of tests/test_gpu_multi.py run kernels that WAIT for kernels of other streams: every stream needs its own
+# hardware queue (default: 8 connections shared by all streams).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE = os.path.join(ROOT, "oracle")
 GOLDEN = os.path.join(ROOT, "tests", "golden")

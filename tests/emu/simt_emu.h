@@ -241,6 +241,8 @@ inline void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, ui
   mbar_complete_locked(mb);
 }
 template <int N> inline void cp_wait_group() {}        // cp.async is an immediate copy here
+inline uint32_t lds16u(uint32_t a) { if (a & 1) abort(); uint16_t v; memcpy(&v, smem_at(a, 2), 2); return v; }
+inline void sts16u(uint32_t a, uint32_t v) { if (a & 1) abort(); const uint16_t w = (uint16_t)v; memcpy(smem_at(a, 2), &w, 2); }
 inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline void stg128f(float* p, float a, float b, float c, float d) {
