@@ -5,13 +5,15 @@
 
 Workload (BASELINE.json configs[2]): Caduceus-PS (rcps=true) d_model=256 n_layer=16 seq_len=131072 bf16
 forward, batch 1 per GPU, random-init weights (reference init), synthetic hg38-shaped ids.
-A "step" = one forward over one batch.  N > 1: one process per GPU (torchrun), every rank runs its own sequence
-(the reference's own scaling mode is data-parallel, ref:train.py:629-639) -> "scaling": "weak"; there is no
-data-path collective, only the timing barrier.
+A "step" = one forward over one batch.  N > 1 (one process per GPU, torchrun): ONE sequence of --seqlen tokens per batch row is
+sharded on the sequence axis over the N ranks (`--shard seq`, the default for N > 1; north_star / SURVEY.md §8e) -> "scaling":
+"strong".  The per-layer exchanges (conv halo, boundary state) are stores into the peers' memory over NVLink by this library's own
+kernels (csrc/peer_exchange.cu), and the whole sharded forward replays from ONE CUDA graph per rank; NCCL carries only the timing
+barrier.  `--shard none` runs N independent replicas instead (the reference's own data-parallel mode, ref:train.py:629-639).
 
-`--impl reference` times the reference's CPU path for the same metric: the oracle port of upstream
-`selective_scan_ref` (oracle/mamba_ssm/ops/selective_scan_interface.py) — the CPU implementation BASELINE.json
-names — on a bounded sample, on rank 0 only.
+`--impl reference` times the reference's CPU path for the same metric: the oracle port of upstream `mamba_inner_ref`
+(oracle/mamba_ssm/ops/selective_scan_interface.py: conv + SiLU, x_proj, dt_proj, `selective_scan_ref`, out_proj — the operator the
+GPU arm fuses) at L = 4096 on all host threads, rank 0 only; the GPU arm's `cpu_baseline` leg times the SAME sample.
 """
 import argparse
 import json
@@ -46,13 +48,16 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: MLM step = forward + loss + backward + AdamW under bf16 autocast (BASELINE configs[3] on 1 GPU)")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay the forward from a CUDA graph (single-GPU / replica forward only; helps short sequences)")
-    ap.add_argument("--scan-tok", type=int, default=0, choices=[0, 8, 16], help="tokens per lane of the scan kernel (tuning)")
-    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 4, 7, 9, 10, 11, 12, 20, 21, 22, 23],
-                    help="forward-scan kernel variant (cad_scan_fwd_args.variant); default: env CAD_SCAN_VARIANT / library default")
-    ap.add_argument("--shard", default="none", choices=["none", "seq"],
-                    help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling)")
+    ap.add_argument("--graph", action="store_true", help="replay the forward from a CUDA graph (default for the sharded forward)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches even for the sharded forward")
+    ap.add_argument("--scan-variant", type=int, default=None, choices=[0, 3, 20],
+                    help="force the forward-scan kernel (cad_scan_fwd_args.variant); default: chosen per call (CF.choose_scan_variant)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "none", "seq"],
+                    help="seq: ONE sequence of --seqlen sharded on the sequence axis over all ranks (strong scaling; auto = seq "
+                         "when N > 1); none: independent replicas")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="sharded forward: halo / boundary-state exchange through NVLink peer memory (this library's kernels) or "
+                         "NCCL all_gather (training always uses NCCL)")
     return ap.parse_args()
 
 
@@ -70,26 +75,34 @@ def scans_per_nt(a):
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of selective_scan_ref
 # ---------------------------------------------------------------------------------------------------------
-def cpu_scan_rate(seconds_budget, L=2048, E=512, N=16, min_calls=1):
-    """token-directions/s of the restated selective_scan_ref (fp32, all host threads), bounded sample."""
+CPU_SAMPLE_L = 4096
+
+
+def cpu_inner_rate(seconds_budget, d_model=256, min_calls=1):
+    """token-directions/s of the oracle's mamba_inner_ref (conv + SiLU -> x_proj -> dt_proj -> selective_scan_ref -> out_proj;
+    fp32, all host threads) on ONE fixed sample: B = 1, L = 4096, E = 2 * d_model, N = 16.  Used by both arms."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from mamba_ssm.ops.selective_scan_interface import selective_scan_ref
+    from mamba_ssm.ops.selective_scan_interface import mamba_inner_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    L, E, N, D = CPU_SAMPLE_L, 2 * d_model, 16, d_model
+    R = (D + 15) // 16
     g = torch.Generator().manual_seed(0)
-    u, z = torch.randn(1, E, L, generator=g), torch.randn(1, E, L, generator=g)
-    Bm, Cm = torch.randn(1, N, L, generator=g), torch.randn(1, N, L, generator=g)
-    delta = 0.5 * torch.rand(1, E, L, generator=g)
+    xz = torch.randn(1, 2 * E, L, generator=g)
+    conv_w, conv_b = 0.5 * torch.randn(E, 1, 4, generator=g), 0.1 * torch.randn(E, generator=g)
+    w_x, w_dt = torch.randn(R + 2 * N, E, generator=g) * E ** -0.5, torch.randn(E, R, generator=g) * R ** -0.5
+    w_out = torch.randn(D, E, generator=g) * E ** -0.5
     A = -torch.arange(1, N + 1, dtype=torch.float32).repeat(E, 1)
-    D, dbias = torch.ones(E), 0.5 * torch.rand(E, generator=g)
+    Dp, dbias = torch.ones(E), torch.log(torch.expm1(torch.exp(torch.rand(E, generator=g) * 4.6 - 6.9)))
     calls, t_total = 0, 0.0
     while calls < min_calls or t_total < seconds_budget:
         t0 = time.perf_counter()
-        selective_scan_ref(u, delta, A, Bm, Cm, D, z, dbias, delta_softplus=True)
+        mamba_inner_ref(xz, conv_w, conv_b, w_x, w_dt, w_out, None, A, None, None, Dp, delta_bias=dbias, delta_softplus=True)
         t_total += time.perf_counter() - t0
         calls += 1
-    return calls * L / t_total, cores, f"{calls} x selective_scan_ref(B=1, E={E}, N={N}, L={L}) fp32, {cores} threads"
+    return calls * L / t_total, cores, (f"{calls} x mamba_inner_ref(B=1, D={D}, E={E}, N={N}, L={L}) fp32, {cores} threads "
+                                        "(conv + x_proj + dt_proj + selective_scan_ref + out_proj)")
 
 
 def run_reference(a):
@@ -100,7 +113,7 @@ def run_reference(a):
     sample = ""
     for i in range(a.warmup + a.steps):
         t0 = time.perf_counter()
-        rate, cores, sample = cpu_scan_rate(0.0, L=2048)
+        rate, cores, sample = cpu_inner_rate(0.0, a.d_model)
         dt = time.perf_counter() - t0
         if i >= a.warmup:
             per_step.append(dt)
@@ -112,8 +125,10 @@ def run_reference(a):
         "ms_per_step": 1e3 * sum(per_step) / len(per_step), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": workload_name(a),
-                   "note": "CPU oracle port of upstream selective_scan_ref (scan only, no projections/conv/norm); "
-                           f"nt/s = token-directions/s / {scans_per_nt(a)} scans per nucleotide"},
+                   "same_config": False,
+                   "note": "CPU oracle port of upstream mamba_inner_ref (one Mamba direction: conv, projections, scan; no norm / "
+                           f"embedding / head) on a fixed L={CPU_SAMPLE_L} sample; nt/s = token-directions/s / {scans_per_nt(a)} "
+                           "Mamba passes per nucleotide — context for the GPU number, not a like-for-like arm"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"per step: {sample}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -172,7 +187,6 @@ def run_b200(a):
     if a.scan_variant is not None:
         CF.SCAN_VARIANT = a.scan_variant
 
-    CF.SCAN_TOKENS_PER_LANE = a.scan_tok
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -208,10 +222,18 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    shard_seq = a.shard == "seq" and world > 1
+    shard_seq = a.shard in ("seq", "auto") and world > 1
+    peer = None
     if shard_seq:       # every rank holds tokens [rank*L/P, (rank+1)*L/P) of the SAME sequences
         from caduceus_b200 import seqshard
+        assert a.seqlen % world == 0, "--seqlen must be a multiple of the number of ranks"
         Ls = a.seqlen // world
+        if not train and a.exchange == "peer":
+            # halo / boundary-state exchange through the peers' memory over NVLink (csrc/peer_exchange.cu): no collective on the
+            # data path, and the whole sharded forward is capturable in one CUDA graph
+            nstrand = 2 if a.model == "ps" else 1
+            peer = seqshard.PeerExchange.create(nseq_max=a.batch * nstrand, njobs_max=a.batch * nstrand * 2, E=2 * a.d_model, N=16,
+                                                device=dev)
         host_ids = [make_ids(torch, a.batch, a.seqlen, 100 + i)[:, rank * Ls:(rank + 1) * Ls].contiguous().pin_memory()
                     for i in range(nbuf)]
         dev_ids = [h.to(dev) for h in host_ids]
@@ -219,7 +241,7 @@ def run_b200(a):
         _model = model
 
         def model(ids):          # noqa: F811  (sequence-parallel wrapper around the same module)
-            with seqshard.sequence_parallel():
+            with seqshard.sequence_parallel(peer=peer):
                 return _model(ids)
 
     def mlm(ids):        # 15 % positions: 80 % [MASK], 10 % random, 10 % kept; target PAD elsewhere
@@ -293,7 +315,9 @@ def run_b200(a):
         step_e2e(i)
 
     graphed = False
-    if a.graph and not train and not shard_seq:
+    # CUDA-graph replay: on request for the single-GPU / replica forward, by default for the peer-exchange sharded forward (its
+    # per-rank GPU work per layer is a fraction of a millisecond: eager launches would bound the step by the host)
+    if not train and not a.no_graph and (a.graph or peer is not None):
         from caduceus_b200.graphs import GraphedForward
         CF.LAUNCHES = 0
         step_device(0)
@@ -322,6 +346,18 @@ def run_b200(a):
     launches = launches_per_step * a.steps if graphed else CF.LAUNCHES     # a replayed graph re-runs the captured launches
     scan_events, CF.SCAN_EVENTS = (CF.SCAN_EVENTS or []), None
     ms_e2e = timed(step_e2e, a.steps)
+    scan_timed_in = "the timed region"
+    if graphed:
+        # events cannot be recorded inside a replayed graph: time the scan launches of two EAGER steps after the timed regions
+        # (same kernels, same shapes; every rank runs them — the sharded forward exchanges with its peers)
+        CF.SCAN_EVENTS = []
+        barrier()
+        with torch.no_grad():
+            for i in range(2):
+                model(dev_ids[i % nbuf])
+        torch.cuda.synchronize()
+        scan_events, CF.SCAN_EVENTS = CF.SCAN_EVENTS, None
+        scan_timed_in = "2 eager steps after the timed region (the timed steps replay a CUDA graph)"
     if sampler:
         sampler.stop_flag.set()
         sampler.join()
@@ -335,10 +371,12 @@ def run_b200(a):
         # 2*(8E+4N) B per nucleotide per BiMamba call; a PS launch covers both strands = 2 calls.
         E, N = 2 * a.d_model, 16
         calls_per_launch = 2 if a.model == "ps" else 1
-        bytes_per_launch = 2 * (8 * E + 4 * N) * calls_per_launch * a.batch * a.seqlen
+        L_launch = a.seqlen // world if shard_seq else a.seqlen                # tokens one launch of THIS rank covers
+        bytes_per_launch = 2 * (8 * E + 4 * N) * calls_per_launch * a.batch * L_launch
         scan_ms = [s.elapsed_time(e) for s, e in scan_events]
-        scan_v4 = CF.SCAN_VARIANT == 4 and not train and not shard_seq      # v4 covers the plain inference call only
         avg_scan_ms = sum(scan_ms) / max(len(scan_ms), 1)
+        nstrand = 2 if a.model == "ps" else 1
+        v_run = 3 if train else CF.choose_scan_variant(torch.bfloat16, N, a.batch * nstrand * 2, E, L_launch)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -350,27 +388,23 @@ def run_b200(a):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
             if a.seqlen == 131072 and a.d_model == 256 and a.batch == 1 and not shard_seq:
-                # measured traffic exists per kernel variant: no entry for the running variant -> null, not another kernel's number
-                v_run = 4 if scan_v4 else (CF.SCAN_VARIANT if (CF.SCAN_VARIANT and not train) else 3)
+                # measured traffic exists per kernel: no entry for the running kernel -> null, not another kernel's number
                 traffic = tj.get(a.model + ("" if v_run == 3 else f"_v{v_run}"), {}).get("dram_bytes_per_launch")
         except Exception:
             pass
-        plain = not train and not shard_seq           # the non-default variants cover the plain inference call
-        kname = ("bimamba_scan_fwd_v4_kernel" if scan_v4 else
-                 "bimamba_scan_fwd_v9_kernel" if CF.SCAN_VARIANT in (9, 10) and plain else
-                 "bimamba_scan_fwd_v11_kernel" if CF.SCAN_VARIANT in (11, 12) and plain else
-                 "bimamba_scan_fwd_v20_kernel (+ bc_transpose, seg_carry, scan_fixup: the whole segmented scan is timed)"
-                 if CF.SCAN_VARIANT >= 20 and plain else "bimamba_scan_fwd_kernel")
+        kname = ("bimamba_scan_fwd_v20_kernel + seg_carry_kernel + scan_fixup_kernel (lane = channel: the whole segmented scan is timed)"
+                 if v_run == 20 else "bimamba_scan_fwd_kernel (one channel per warp, time-parallel)")
         roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "6.65 TB/s (of fallback)",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_scan_ms,
-                "launches_timed": len(scan_ms), "share_of_step": avg_scan_ms * len(scan_ms) / ms_dev if scan_ms else None}
+                "launches_timed": len(scan_ms), "timed_in": scan_timed_in,
+                "share_of_step": (avg_scan_ms * a.n_layer) / (ms_dev / a.steps) if scan_ms else None}
         # the pipe that actually binds the scan: MUFU ex2, one per (token, channel, state)
         try:
             mufu = CF.microbench(0)
-            ex2_per_launch = E * N * 2 * calls_per_launch * a.batch * a.seqlen
+            ex2_per_launch = E * N * 2 * calls_per_launch * a.batch * L_launch
             roof["mufu"] = {"ex2_per_s_measured_peak": mufu, "ffma_per_s_measured_peak": CF.microbench(1),
                             "achieved_scan_ex2_per_s": ex2_per_launch / (avg_scan_ms * 1e-3) if scan_ms else None}
             if scan_ms:
@@ -380,23 +414,27 @@ def run_b200(a):
 
         cpu = None
         if not a.no_cpu_baseline:
-            rate, cores, sample = cpu_scan_rate(12.0, L=4096, min_calls=2)
+            rate, cores, sample = cpu_inner_rate(12.0, a.d_model, min_calls=2)
             cpu = {"value": rate / scans_per_nt(a), "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": sample + f"; nt/s = token-directions/s / {scans_per_nt(a)} (scan only)",
+                   "sample": sample + f"; nt/s = token-directions/s / {scans_per_nt(a)} Mamba passes per nucleotide",
                    "token_directions_per_s": rate}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
             "scaling": "strong" if shard_seq else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "mode": a.mode,
-            "config": {"workload": workload_name(a), "parallelism": (f"sp{world} (one sequence sharded on the sequence axis, 2 tiny all_gathers per layer)"
+            "config": {"workload": workload_name(a),
+                       "parallelism": ((f"sp{world}: one sequence per batch row sharded on the sequence axis; per layer one conv-halo and "
+                                        "one boundary-state exchange, " +
+                                        ("stores into the peers' memory over NVLink by the library's own kernels, no collective"
+                                         if peer is not None else "NCCL all_gather"))
                                        if shard_seq else f"dp{world} (independent sequences per GPU)"),
                        "l2": "per-step working set > 1 GB >> 126 MB L2; 4 rotating input batches",
                        "launch": "CUDA graph replay" if graphed else "eager",
-                       "scan_variant": 4 if scan_v4 else (CF.SCAN_VARIANT or 3)},
+                       "scan_variant": v_run},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
-                    "h2d_bytes_per_step": a.batch * a.seqlen * 8 * world,
-                    "d2h_bytes_per_step": (4 if train else a.batch * a.seqlen * cfg.vocab_size * 4) * world},
+                    "h2d_bytes_per_step": a.batch * a.seqlen * 8 * (1 if shard_seq else world),
+                    "d2h_bytes_per_step": (4 * world if train else a.batch * a.seqlen * cfg.vocab_size * 4 * (1 if shard_seq else world))},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,

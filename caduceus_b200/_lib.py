@@ -52,8 +52,7 @@ class ScanFwdArgs(C.Structure):
                 ("L", _i64), ("E", _i64), ("N", _i64), ("K", _i64),
                 ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
                 ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
-                ("state_only", _i32), ("tokens_per_lane", _i32), ("variant", _i32),
-                ("bc16", _p), ("ldbc16", _i64), ("delta_is_dt", _i32),
+                ("state_only", _i32), ("variant", _i32),
                 ("bcT", _p), ("nseg", _i32), ("seg_state", _p), ("seg_dtsum", _p)]
 
 
@@ -83,8 +82,7 @@ class ScanBwdArgs(C.Structure):
                 ("L", _i64), ("E", _i64), ("N", _i64), ("K", _i64),
                 ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64), ("lddz", _i64), ("lddu", _i64),
                 ("lddd", _i64),
-                ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
-                ("variant", _i32)]
+                ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32)]
 
 
 class ConvBwdArgs(C.Structure):
@@ -106,7 +104,7 @@ class ConvXprojArgs(C.Structure):
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
                 ("delta", _p), ("bc", _p),
                 ("L", _i64), ("E", _i64), ("N", _i64), ("R", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64),
-                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bc16", _p), ("ldbc16", _i64), ("dt_b", _p), ("bcT", _p), ("ldT", _i64)]
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bcT", _p), ("ldT", _i64)]
 
 
 class ConvFwdArgs(C.Structure):

@@ -12,7 +12,6 @@
 // Outputs: dz, d dt_raw, du (gradient w.r.t. the conv+SiLU output, finished by conv_bwd after the x_proj GEMM
 // gradient has been added), dB/dC, parameter gradients, optional dh0.
 #include "scan_common.cuh"
-#include "scan_bwd_v2.cuh"
 
 namespace cad {
 
@@ -407,29 +406,6 @@ static int launch_scan_bwd(const cad_scan_bwd_args& a, int G, cudaStream_t strea
   return 0;
 }
 
-// ---- variant 2 (scan_bwd_v2.cuh): 8 tokens per lane, two 256-token passes per saved chunk, 128 registers so that TWO
-//      7-warp CTAs share an SM (smem: 64 KB tile + 28 KB slots + 16 KB partials = 109 KB per CTA)
-template <typename T>
-__global__ void __launch_bounds__(bw2::kMaxG * 32, 2)
-bimamba_scan_bwd_v2_kernel(const cad_scan_bwd_args a, const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ unsigned char smem_raw[];
-  bw2::kernel_body<T>(a, &tmap, smem_raw);
-}
-
-template <typename T>
-static int launch_scan_bwd_v2(const cad_scan_bwd_args& a, int G, cudaStream_t stream) {
-  CUtensorMap tmap;
-  if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * bw2::NST, a.ldbc, a.L, 2 * bw2::NST, bw2::CH) != 0) return -1;
-  const size_t smem = bw2::smem_bytes();
-  CAD_REQUIRE(smem <= 227 * 1024 / 2, "cad_bimamba_scan_bwd(v2): %zu B of shared memory do not fit twice per SM", smem);
-  auto kern = bimamba_scan_bwd_v2_kernel<T>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(bwd v2): %s", cudaGetErrorString(e)); return (int)e; }
-  dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
-  kern<<<grid, G * 32, smem, stream>>>(a, tmap);
-  CAD_LAUNCH_CHECK();
-  return 0;
-}
 
 // ---- conv + SiLU backward ---------------------------------------------------------------------------------------------
 //   c[tau] = b + sum_k w[k] x[tau-3+k],  u = silu(c);   given du:  dc = du * silu'(c)
@@ -544,11 +520,6 @@ extern "C" int cad_bimamba_scan_bwd(const cad_scan_bwd_args* a, void* stream_) {
     }
   }
   CAD_REQUIRE(G >= 1 && G <= kMaxG, "cad_bimamba_scan_bwd: channels_per_cta must be in [1, %d]", kMaxG);
-  CAD_REQUIRE(a->variant == 0 || a->variant == 1 || a->variant == 2, "cad_bimamba_scan_bwd: unknown variant %d",
-              (int)a->variant);
-  if (a->variant == 2) {
-    CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan_bwd_v2<T>(*a, G, stream));
-  }
   CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan_bwd<T, 16>(*a, G, stream));
   return 0;
 }

@@ -25,7 +25,7 @@ constexpr int kRing = 4;             // cp.async stages per warp (1 KB each: 32 
 constexpr int kMaxW = 4;             // warps (channels) per CTA: small CTAs, so that a slow channel does not pin the slots of retired warps
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc));   // .ca: the CTA's warps share the C rows through L1
 }
 
 template <typename T> struct Raw8;                                   // 8 elements as they lie in memory
@@ -74,7 +74,7 @@ template <typename T, int N, bool REV>
 __device__ __forceinline__ void fixup_warp(const cad_scan_fixup_args& a, int job, int seq, int pset, int64_t t_off, int64_t Lr64,
                                            const float* __restrict__ h0_base, int64_t ch, uint32_t ring_base) {
   const int lane = threadIdx.x & 31;
-  const uint32_t ring = ring_base + (uint32_t)(threadIdx.x >> 5) * (kRing * 1024u) + (uint32_t)lane * 16u;
+  const uint32_t ring = ring_base + (uint32_t)(threadIdx.x >> 5) * (kRing * 1024u + 2048u) + (uint32_t)lane * 16u;
   const int64_t E = a.E;
   const int64_t pc = (int64_t)pset * E + ch;
   // lane n < 16 keeps (A2[n], h0[n]) of this channel; broadcast per state with a shuffle
@@ -107,7 +107,16 @@ __device__ __forceinline__ void fixup_warp(const cad_scan_fixup_args& a, int job
     const bool in = ts < Lr;
     float dr[FT];
     if (in) unpack8<T>(d_raw, dr);
-    // dt_raw of the next step is requested now and flies during the state loop
+    // z / out of this step (into this warp's two extra ring slots: no registers) and dt_raw of the next are requested now and
+    // fly during the state loop; they belong to the first cp.async group of the step
+    if (in) {
+      constexpr int PIECES = (int)sizeof(T) * FT / 16;         // 16-byte pieces per lane and row: 1 (16-bit) or 2 (fp32)
+#pragma unroll
+      for (int h = 0; h < PIECES; ++h) {
+        cp_async16(ring + kRing * 1024u + 512u * h, reinterpret_cast<const char*>(zrow + ts) + 16 * h);
+        cp_async16(ring + kRing * 1024u + 1024u + 512u * h, reinterpret_cast<const char*>(orow + ts) + 16 * h);
+      }
+    }
     const int ts_next = c + 1 < nsteps ? tok0(c + 1) : Lr;
     if (ts_next < Lr) d_raw = ld8<T>(drow + ts_next, true);
 
@@ -173,7 +182,14 @@ __device__ __forceinline__ void fixup_warp(const cad_scan_fixup_args& a, int job
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");      // (empty groups only) before the ring is reused by the next step
     if (in) {
-      const Raw8<T> z_raw = ld8<T>(zrow + ts, true), o_raw = ld8<T>(orow + ts, false);
+      Raw8<T> z_raw, o_raw;
+      if constexpr (sizeof(T) == 4) {
+        z_raw.a = lds128(ring + kRing * 1024u); z_raw.b = lds128(ring + kRing * 1024u + 512u);
+        o_raw.a = lds128(ring + kRing * 1024u + 1024u); o_raw.b = lds128(ring + kRing * 1024u + 1536u);
+      } else {
+        const float4 zq = lds128(ring + kRing * 1024u), oq = lds128(ring + kRing * 1024u + 1024u);
+        z_raw.a = *reinterpret_cast<const uint4*>(&zq); o_raw.a = *reinterpret_cast<const uint4*>(&oq);
+      }
       float zs[FT], os[FT];
       unpack8<T>(z_raw, zs);
       unpack8<T>(o_raw, os);
@@ -196,7 +212,7 @@ __device__ __forceinline__ void fixup_warp(const cad_scan_fixup_args& a, int job
 
 template <typename T, int N>
 __global__ void __launch_bounds__(kMaxW * 32, 8) scan_fixup_kernel(const cad_scan_fixup_args a) {
-  __shared__ __align__(16) unsigned char ring_s[kMaxW * kRing * 1024];
+  __shared__ __align__(16) unsigned char ring_s[kMaxW * (kRing * 1024 + 2048)];     // per warp: kRing C rows + z + out of the step
   const uint32_t ring_base = smem_u32(ring_s);
   const int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= a.E) return;                                        // warp-uniform; there is no CTA-level synchronisation

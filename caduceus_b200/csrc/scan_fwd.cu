@@ -28,8 +28,6 @@
 //   profiles: profiles/r1_v1_scan_ncu_summary.txt (v1: 20.8 warp-instructions per element, 43 % issue utilisation)
 //   -> profiles/r1_v3_scan_and_bwd_ncu_summary.txt (11.4 instructions per element, MUFU pipe 53 %, issue 57 %).
 #include "scan_common.cuh"
-#include "scan_fwd_v4.cuh"
-#include "scan_fwd_v9.cuh"
 
 namespace cad {
 
@@ -48,8 +46,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // One chunk of one channel.  TAIL: the chunk straddles the sequence end (per-token masks, halo in the pad).
-// PK: 0 = scalar fp32 state loop with a replay pass (variant 3, the default); 3 = packed token pairs, no replay (variant 7).
-template <typename T, int N, int TOK, bool REV, bool TAIL, bool STATE_ONLY, int PK>
+template <typename T, int N, int TOK, bool REV, bool TAIL, bool STATE_ONLY>
 __device__ __forceinline__ void scan_chunk(
     const cad_scan_fwd_args& a, const ScanSmem& sm, int lane, int seg, const uint32_t (&poff)[TOK / 4],
     const T* __restrict__ xrow, const T* __restrict__ zrow, const T* __restrict__ drow, T* __restrict__ orow,
@@ -127,128 +124,56 @@ __device__ __forceinline__ void scan_chunk(
   mbar_wait(sm.bar, parity);
   const uint32_t tile_s = smem_u32(sm.tile);
   const uint32_t a2_s = smem_u32(my_a2), carry_s = smem_u32(my_carry);
-  if constexpr (PK == 0) {
-  #pragma unroll 1
-    for (int n = 0; n < N; ++n) {
-      const float A2n = lds32(a2_s + 4 * n);
-      const float cin = lds32(carry_s + 4 * n);
-      float av[TOK], bv[TOK];
-      float hl = (lane == 0) ? cin : 0.f;
-      {
-        const uint32_t rowp = tile_s + n * (CH * 4);
-  #pragma unroll
-        for (int k = 0; k < TOK / 4; ++k) {
-          const float4 q = lds128(rowp + poff[k]);
-          const float bq[4] = {q.x, q.y, q.z, q.w};
-  #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;     // logical item of physical token 4k+e
-            av[i] = ex2(dt[i] * A2n);
-            bv[i] = du[i] * bq[e];
-          }
-        }
-  #pragma unroll
-        for (int i = 0; i < TOK; ++i) hl = fmaf(av[i], hl, bv[i]);
-      }
-      float P = ex2(A2n * dsum);
-      scan_step_up<1>(P, hl, lane);
-      scan_step_up<2>(P, hl, lane);
-      scan_step_up<4>(P, hl, lane);
-      scan_step_up<8>(P, hl, lane);
-      scan_step_up<16>(P, hl, lane);
-      float h = __shfl_up_sync(0xffffffffu, hl, 1);
-      if (lane == 0) h = cin;
-      if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
-      if (!STATE_ONLY) {
-        const uint32_t rowp = tile_s + (N + n) * (CH * 4);
-        float4 cq[TOK / 4];
-  #pragma unroll
-        for (int k = 0; k < TOK / 4; ++k) cq[k] = lds128(rowp + poff[k]);
-        // walk the segment in LOGICAL order (physical pieces backwards for a reversed job)
-  #pragma unroll
-        for (int kk = 0; kk < TOK / 4; ++kk) {
-          const int k = REV ? TOK / 4 - 1 - kk : kk;
-          const float ce[4] = {cq[k].x, cq[k].y, cq[k].z, cq[k].w};
-  #pragma unroll
-          for (int ee = 0; ee < 4; ++ee) {
-            const int e = REV ? 3 - ee : ee;
-            const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;
-            h = fmaf(av[i], h, bv[i]);
-            y[i] = fmaf(ce[e], h, y[i]);
-          }
-        }
-      }
-    }
-  } else {
-    // PK 3 — token pairs packed, no replay pass.  Adjacent PHYSICAL tokens of the lane's segment sit in aligned
-    // register pairs (FMUL2 / FFMA2 with the scalar A2 or carry as the broadcast operand).  The zero-state pass also
-    // accumulates y += C.h_local and the running decay pc_t = prod_{s<=t} a_s; after the warp scan the carry-in enters
-    // as 8 INDEPENDENT packed FMAs  y_t += (C_t pc_t) * h_in.  Against the replay form this drops the second 16-step
-    // dependent chain, the stored a / b arrays (32 registers) and the extra exp2 of the segment decay (the aggregate
-    // IS pc_15); it adds one FMUL (pc) and half a packed FMUL (C*pc) per element.  127 instead of 137 instructions
-    // per (lane, state); measured equal to PK 0 on Caduceus-PS and 5 % faster on Caduceus-Ph
-    // (profiles/r1_ab_scan_v3_v7_v8.jsonl) — the loop is bound by MUFU / shuffle latency, not by issue slots.
-    using v4::fma2; using v4::mul2; using v4::splat; using v4::ex2_2;
-    constexpr int NP = TOK / 2;
-    auto lgc = [](int p) { return REV ? TOK - 1 - p : p; };          // physical token of the segment -> logical item
-    float2 dt2[NP], du2[NP], y2[NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      dt2[j] = make_float2(dt[lgc(2 * j)], dt[lgc(2 * j + 1)]);
-      du2[j] = make_float2(du[lgc(2 * j)], du[lgc(2 * j + 1)]);
-      y2[j] = make_float2(y[lgc(2 * j)], y[lgc(2 * j + 1)]);
-    }
 #pragma unroll 1
-    for (int n = 0; n < N; ++n) {
-      const float A2n = lds32(a2_s + 4 * n);
-      const float cin = lds32(carry_s + 4 * n);
-      float hl = 0.f, pc = 1.f;
-      float2 g2[NP];
+  for (int n = 0; n < N; ++n) {
+    const float A2n = lds32(a2_s + 4 * n);
+    const float cin = lds32(carry_s + 4 * n);
+    float av[TOK], bv[TOK];
+    float hl = (lane == 0) ? cin : 0.f;
+    {
+      const uint32_t rowp = tile_s + n * (CH * 4);
 #pragma unroll
-      for (int kk = 0; kk < TOK / 4; ++kk) {                         // 16-byte pieces of the tile rows, logical order
-        const int k = REV ? TOK / 4 - 1 - kk : kk;
-        const float4 bq = lds128(tile_s + n * (CH * 4) + poff[k]);
-        float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!STATE_ONLY) cq = lds128(tile_s + (N + n) * (CH * 4) + poff[k]);
+      for (int k = 0; k < TOK / 4; ++k) {
+        const float4 q = lds128(rowp + poff[k]);
+        const float bq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          const int half = REV ? 1 - jj : jj;                        // pair inside the piece, logical order
-          const int j = 2 * k + half;
-          const float2 bp = half ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y);
-          const float2 av = ex2_2(mul2(dt2[j], splat(A2n)));
-          const float2 bv = mul2(du2[j], bp);
-          float2 hp, pp;
-          if (REV) {
-            hl = fmaf(av.y, hl, bv.y); hp.y = hl; pc *= av.y; pp.y = pc;
-            hl = fmaf(av.x, hl, bv.x); hp.x = hl; pc *= av.x; pp.x = pc;
-          } else {
-            hl = fmaf(av.x, hl, bv.x); hp.x = hl; pc *= av.x; pp.x = pc;
-            hl = fmaf(av.y, hl, bv.y); hp.y = hl; pc *= av.y; pp.y = pc;
-          }
-          if (!STATE_ONLY) {
-            const float2 cp = half ? make_float2(cq.z, cq.w) : make_float2(cq.x, cq.y);
-            y2[j] = fma2(cp, hp, y2[j]);
-            g2[j] = mul2(cp, pp);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;     // logical item of physical token 4k+e
+          av[i] = ex2(dt[i] * A2n);
+          bv[i] = du[i] * bq[e];
         }
       }
-      float P = pc;
-      if (lane == 0) hl = fmaf(pc, cin, hl);                         // the chunk's carry-in enters through lane 0's aggregate
-      scan_step_up<1>(P, hl, lane);
-      scan_step_up<2>(P, hl, lane);
-      scan_step_up<4>(P, hl, lane);
-      scan_step_up<8>(P, hl, lane);
-      scan_step_up<16>(P, hl, lane);
-      float h = __shfl_up_sync(0xffffffffu, hl, 1);
-      if (lane == 0) h = cin;
-      if (lane == 31) sts32(carry_s + 4 * n, hl);                    // state at the end of this chunk
-      if (!STATE_ONLY) {
 #pragma unroll
-        for (int j = 0; j < NP; ++j) y2[j] = fma2(g2[j], splat(h), y2[j]);
+      for (int i = 0; i < TOK; ++i) hl = fmaf(av[i], hl, bv[i]);
+    }
+    float P = ex2(A2n * dsum);
+    scan_step_up<1>(P, hl, lane);
+    scan_step_up<2>(P, hl, lane);
+    scan_step_up<4>(P, hl, lane);
+    scan_step_up<8>(P, hl, lane);
+    scan_step_up<16>(P, hl, lane);
+    float h = __shfl_up_sync(0xffffffffu, hl, 1);
+    if (lane == 0) h = cin;
+    if (lane == 31) sts32(carry_s + 4 * n, hl);          // state at the end of this chunk
+    if (!STATE_ONLY) {
+      const uint32_t rowp = tile_s + (N + n) * (CH * 4);
+      float4 cq[TOK / 4];
+#pragma unroll
+      for (int k = 0; k < TOK / 4; ++k) cq[k] = lds128(rowp + poff[k]);
+      // walk the segment in LOGICAL order (physical pieces backwards for a reversed job)
+#pragma unroll
+      for (int kk = 0; kk < TOK / 4; ++kk) {
+        const int k = REV ? TOK / 4 - 1 - kk : kk;
+        const float ce[4] = {cq[k].x, cq[k].y, cq[k].z, cq[k].w};
+#pragma unroll
+        for (int ee = 0; ee < 4; ++ee) {
+          const int e = REV ? 3 - ee : ee;
+          const int i = REV ? TOK - 1 - (4 * k + e) : 4 * k + e;
+          h = fmaf(av[i], h, bv[i]);
+          y[i] = fmaf(ce[e], h, y[i]);
+        }
       }
     }
-#pragma unroll
-    for (int j = 0; j < NP; ++j) { y[lgc(2 * j)] = y2[j].x; y[lgc(2 * j + 1)] = y2[j].y; }
   }
 
   // ---- 4. hand the tile back: everyone is done reading -> request the next chunk -------------------------
@@ -276,7 +201,7 @@ __device__ __forceinline__ void scan_chunk(
   (void)EPV;
 }
 
-template <typename T, int N, int TOK, bool REV, bool STATE_ONLY, int PK>
+template <typename T, int N, int TOK, bool REV, bool STATE_ONLY>
 __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUtensorMap* tmap, int job, int seq,
                                          int pset, const ScanSmem& sm) {
   constexpr int CH = 32 * TOK;
@@ -366,11 +291,11 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     const T* pre_cur = pre_ptr((int)(c & 1));
     T* pre_next = pre_ptr((int)((c + 1) & 1));
     if (tail)
-      scan_chunk<T, N, TOK, REV, true, STATE_ONLY, PK>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, TOK, REV, true, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                   prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
                                   tseg_next);
     else
-      scan_chunk<T, N, TOK, REV, false, STATE_ONLY, PK>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
+      scan_chunk<T, N, TOK, REV, false, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                    prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
                                    tseg_next);
     parity ^= 1;
@@ -391,7 +316,7 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
   }
 }
 
-template <typename T, int N, int TOK, bool STATE_ONLY, int PK>
+template <typename T, int N, int TOK, bool STATE_ONLY>
 __device__ __forceinline__ void scan_kernel_body(const cad_scan_fwd_args& a, const CUtensorMap* tmap) {
   extern __shared__ unsigned char smem_raw[];
   // the swizzled TMA destination must be 1024-byte aligned
@@ -406,17 +331,17 @@ __device__ __forceinline__ void scan_kernel_body(const cad_scan_fwd_args& a, con
   if (threadIdx.x == 0) mbar_init(sm.bar, 1);
   const int job = blockIdx.y;
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
-  if (rev) scan_job<T, N, TOK, true, STATE_ONLY, PK>(a, tmap, job, seq, pset, sm);
-  else     scan_job<T, N, TOK, false, STATE_ONLY, PK>(a, tmap, job, seq, pset, sm);
+  if (rev) scan_job<T, N, TOK, true, STATE_ONLY>(a, tmap, job, seq, pset, sm);
+  else     scan_job<T, N, TOK, false, STATE_ONLY>(a, tmap, job, seq, pset, sm);
 }
 
-template <typename T, int N, int TOK, bool STATE_ONLY, int PK = 0>
+template <typename T, int N, int TOK, bool STATE_ONLY>
 __global__ void __launch_bounds__(kMaxG * 32, (TOK == 16 ? 2 : 4))
 bimamba_scan_fwd_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
-  scan_kernel_body<T, N, TOK, STATE_ONLY, PK>(a, &tmap);
+  scan_kernel_body<T, N, TOK, STATE_ONLY>(a, &tmap);
 }
 
-template <typename T, int N, int TOK, int PK = 0>
+template <typename T, int N, int TOK>
 static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
   constexpr int CH = 32 * TOK;
   CUtensorMap tmap;
@@ -424,80 +349,9 @@ static int launch_scan(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
 
   const size_t pre_bytes = sizeof(T) == 2 ? (size_t)2 * G * 3 * CH * sizeof(T) : 0;
   const size_t smem = 1024 + (size_t)2 * N * CH * 4 + (size_t)2 * kMaxG * N * sizeof(float) + 16 + pre_bytes;
-  auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, TOK, true, PK> : bimamba_scan_fwd_kernel<T, N, TOK, false, PK>;
+  auto kern = a.state_only ? bimamba_scan_fwd_kernel<T, N, TOK, true> : bimamba_scan_fwd_kernel<T, N, TOK, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
-  kern<<<grid, G * 32, smem, stream>>>(a, tmap);
-  CAD_LAUNCH_CHECK();
-  return 0;
-}
-
-// ---- v4: two channels per warp, packed fp32 (scan_fwd_v4.cuh) ------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(v4::kMaxG4 * 32, 1)
-bimamba_scan_fwd_v4_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ unsigned char smem_raw[];
-  v4::kernel_body<T>(a, &tmap, smem_raw);
-}
-
-template <typename T>
-static int launch_scan_v4(const cad_scan_fwd_args& a, int G, cudaStream_t stream) {
-  CUtensorMap tmap;
-  if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * v4::NST, a.ldbc, a.L, 2 * v4::NST, v4::CH) != 0) return -1;
-  const size_t smem = v4::smem_bytes(G, sizeof(T));
-  auto kern = bimamba_scan_fwd_v4_kernel<T>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(v4): %s", cudaGetErrorString(e)); return (int)e; }
-  const int64_t npair = a.E / 2;
-  dim3 grid((unsigned)((npair + G - 1) / G), (unsigned)a.njobs);
-  kern<<<grid, G * 32, smem, stream>>>(a, tmap);
-  CAD_LAUNCH_CHECK();
-  return 0;
-}
-
-// v4 covers the inference configuration only (see scan_fwd_v4.cuh "scope")
-static bool v4_supported(const cad_scan_fwd_args& a) {
-  return a.io_dtype != CAD_F32 && a.N == v4::NST && a.E % 2 == 0 && !a.halo && !a.h0 && !a.hlast && !a.dtsum &&
-         !a.chunk_state && !a.state_only && (a.tokens_per_lane == 0 || a.tokens_per_lane == 16);
-}
-
-// ---- v9 .. v12: barrier-free tile hand-over, no replay, optional exp2 pipeline (scan_fwd_v9.cuh) ----------------------
-//      9 / 10: 16-bit tile, <= 7 warps, two CTAs per SM;   11 / 12: fp32 tile shared by <= 14 warps, one CTA per SM
-template <typename T, bool STATE_ONLY, bool PIPE>
-__global__ void __launch_bounds__(7 * 32, 2)
-bimamba_scan_fwd_v9_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ unsigned char smem_raw[];
-  v9::kernel_body<T, T, STATE_ONLY, PIPE>(a, &tmap, smem_raw);
-}
-// 14 warps must fit the register file of ONE SM partition-wise: 4 warps x 32 x 128 = 16 K registers per scheduler
-template <typename T, bool STATE_ONLY, bool PIPE>
-__global__ void __maxnreg__(128)
-bimamba_scan_fwd_v11_kernel(const cad_scan_fwd_args a, const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ unsigned char smem_raw[];
-  v9::kernel_body<T, float, STATE_ONLY, PIPE>(a, &tmap, smem_raw);
-}
-
-template <typename T>
-static int launch_scan_v9(const cad_scan_fwd_args& a, int G, bool pipe, bool tile32, cudaStream_t stream) {
-  CUtensorMap tmap;
-  if (tile32) {
-    if (make_row_tile_map(&tmap, a.bc, (int64_t)a.njobs * 2 * v9::NST, a.ldbc, a.L, 2 * v9::NST, v9::CH) != 0) return -1;
-  } else {
-    if (make_row_tile_map16(&tmap, a.bc16, a.io_dtype == CAD_BF16, (int64_t)a.njobs * 2 * v9::NST, a.ldbc16, a.L,
-                            2 * v9::NST, v9::CH) != 0) return -1;
-  }
-  const size_t smem = v9::smem_bytes(G, sizeof(T), tile32 ? 4 : sizeof(T));
-  void (*kern)(const cad_scan_fwd_args, const CUtensorMap);
-  if (tile32) {
-    if (a.state_only) kern = pipe ? bimamba_scan_fwd_v11_kernel<T, true, true> : bimamba_scan_fwd_v11_kernel<T, true, false>;
-    else              kern = pipe ? bimamba_scan_fwd_v11_kernel<T, false, true> : bimamba_scan_fwd_v11_kernel<T, false, false>;
-  } else {
-    if (a.state_only) kern = pipe ? bimamba_scan_fwd_v9_kernel<T, true, true> : bimamba_scan_fwd_v9_kernel<T, true, false>;
-    else              kern = pipe ? bimamba_scan_fwd_v9_kernel<T, false, true> : bimamba_scan_fwd_v9_kernel<T, false, false>;
-  }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(v9): %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)((a.E + G - 1) / G), (unsigned)a.njobs);
   kern<<<grid, G * 32, smem, stream>>>(a, tmap);
   CAD_LAUNCH_CHECK();
@@ -515,8 +369,8 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
   CAD_REQUIRE(a, "cad_bimamba_scan_fwd: null argument block");
   CAD_REQUIRE(a->L >= 0 && a->E > 0 && a->njobs > 0 && a->nseq > 0, "cad_bimamba_scan_fwd: bad sizes");
   if (a->L == 0) return 0;
-  CAD_REQUIRE(a->xz && a->delta && (a->bc || a->variant == 9 || a->variant == 10 || a->variant >= 20) && (a->out || a->state_only) && a->conv_w && a->conv_b && a->dt_b && a->A2 && a->Dskip &&
-              a->seq_of_job && a->pset_of_job && a->rev_of_job, "cad_bimamba_scan_fwd: null pointer");
+  CAD_REQUIRE(a->xz && a->delta && (a->bc || a->variant == 20) && (a->out || a->state_only) && a->conv_w && a->conv_b && a->dt_b &&
+              a->A2 && a->Dskip && a->seq_of_job && a->pset_of_job && a->rev_of_job, "cad_bimamba_scan_fwd: null pointer");
   CAD_REQUIRE(a->N == 16, "cad_bimamba_scan_fwd: d_state = %lld not built (only 16)", (long long)a->N);
   CAD_REQUIRE(a->K >= 1 && a->K <= 4, "cad_bimamba_scan_fwd: d_conv = %lld out of range [1, 4]", (long long)a->K);
   CAD_REQUIRE(a->ldxz % 16 == 0 && a->ldd % 16 == 0 && a->ldo % 16 == 0 && a->ldxz >= a->L && a->ldd >= a->L &&
@@ -526,28 +380,8 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
               "cad_bimamba_scan_fwd: xz/delta/bc/out must be 16-byte aligned");
   CAD_REQUIRE(!a->state_only || (a->hlast && a->dtsum), "cad_bimamba_scan_fwd: state_only needs hlast and dtsum");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 4 || a->variant == 7 || (a->variant >= 9 && a->variant <= 12) ||
-              (a->variant >= 20 && a->variant <= 23), "cad_bimamba_scan_fwd: variant must be 0, 3, 4, 7, 9..12 or 20..23");
-  CAD_REQUIRE(!a->delta_is_dt || (a->variant >= 9 && a->io_dtype != CAD_F32 && !a->chunk_state),
-              "cad_bimamba_scan_fwd: delta_is_dt needs variant 9..12 or 20, 16-bit I/O and no saved chunk states (inference)");
-  if (a->variant >= 20) return launch_scan_v20(*a, stream);
-  if (a->variant == 4) {
-    CAD_REQUIRE(v4_supported(*a), "cad_bimamba_scan_fwd: variant 4 needs 16-bit I/O, d_state 16, even E and none of "
-                "halo / h0 / hlast / dtsum / chunk_state / state_only");
-    int G4 = a->channels_per_cta;       // here: channel PAIRS (warps) per CTA
-    if (G4 <= 0) {
-      const int sms = cad_sm_count() > 0 ? cad_sm_count() : 148;
-      long best = -1;
-      for (int g = 1; g <= v4::kMaxG4; ++g) {      // one CTA per SM: minimise the busiest SM's pair count
-        const long ctas = (long)a->njobs * ((a->E / 2 + g - 1) / g);
-        const long cost = ((ctas + sms - 1) / sms) * g;
-        if (best < 0 || cost <= best) { best = cost; G4 = g; }
-      }
-    }
-    CAD_REQUIRE(G4 >= 1 && G4 <= v4::kMaxG4, "cad_bimamba_scan_fwd: channels_per_cta must be in [1, %d] for variant 4", v4::kMaxG4);
-    if (a->io_dtype == CAD_BF16) return launch_scan_v4<__nv_bfloat16>(*a, G4, stream);
-    return launch_scan_v4<__half>(*a, G4, stream);
-  }
+  CAD_REQUIRE(a->variant == 0 || a->variant == 3 || a->variant == 20, "cad_bimamba_scan_fwd: variant must be 0, 3 or 20");
+  if (a->variant == 20) return launch_scan_v20(*a, stream);
   int G = a->channels_per_cta;
   if (G <= 0) {
     // two CTAs are resident per SM; the busiest SM carries ceil(ctas / sms) * g channels: minimise that
@@ -560,36 +394,6 @@ extern "C" int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream_) {
     }
   }
   CAD_REQUIRE(G >= 1 && G <= kMaxG, "cad_bimamba_scan_fwd: channels_per_cta must be in [1, %d]", kMaxG);
-  if (a->variant >= 9) {
-    const bool tile32 = a->variant >= 11, pipe = (a->variant == 10 || a->variant == 12);
-    CAD_REQUIRE(a->io_dtype != CAD_F32, "cad_bimamba_scan_fwd: variants 9..12 need 16-bit I/O");
-    CAD_REQUIRE(tile32 || (a->bc16 && aligned16(a->bc16) && a->ldbc16 % 64 == 0 && a->ldbc16 >= a->L),
-                "cad_bimamba_scan_fwd: variants 9 / 10 need bc16 (16-byte aligned, ldbc16 a multiple of 64 and >= L)");
-    int G9 = a->channels_per_cta;
-    const int gmax = tile32 ? v9::kMaxG9 : 7;
-    if (G9 <= 0) {
-      const int sms = cad_sm_count() > 0 ? cad_sm_count() : 148;
-      const int per_sm = tile32 ? 1 : 2;       // resident CTAs per SM
-      long best = -1;
-      for (int g = 1; g <= gmax; ++g) {
-        const long ctas = (long)a->njobs * ((a->E + g - 1) / g);
-        const long cost = ((ctas + (long)sms * per_sm - 1) / ((long)sms * per_sm)) * g;
-        if (best < 0 || cost <= best) { best = cost; G9 = g; }
-      }
-    }
-    CAD_REQUIRE(G9 >= 1 && G9 <= gmax, "cad_bimamba_scan_fwd: channels_per_cta must be in [1, %d] for this variant", gmax);
-    if (a->io_dtype == CAD_BF16) return launch_scan_v9<__nv_bfloat16>(*a, G9, pipe, tile32, stream);
-    return launch_scan_v9<__half>(*a, G9, pipe, tile32, stream);
-  }
-  // tokens per lane: 16 (512-token chunks, 2 CTAs/SM) or 8 (256-token chunks, up to 4 CTAs/SM, 16-bit I/O only).
-  // The saved chunk states (training) are defined on 512-token chunks, so they force 16.
-  int tok = a->tokens_per_lane;
-  if (tok == 0) tok = 16;
-  CAD_REQUIRE(tok == 16 || tok == 8, "cad_bimamba_scan_fwd: tokens_per_lane must be 0, 8 or 16");
-  if (a->chunk_state || a->io_dtype == CAD_F32) tok = 16;
-  if (tok == 16 && a->variant == 7) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16, 3>(*a, G, stream)); }
-  if (tok == 16) { CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16>(*a, G, stream)); }
-  else if (a->io_dtype == CAD_BF16) return launch_scan<__nv_bfloat16, 16, 8>(*a, G, stream);
-  else return launch_scan<__half, 16, 8>(*a, G, stream);
+  CAD_DISPATCH_DTYPE(a->io_dtype, T, return launch_scan<T, 16, 16>(*a, G, stream));
   return 0;
 }

@@ -5,20 +5,11 @@
 
 namespace cad {
 
-template <typename T, int NPOLY>
+template <typename T>
 __global__ void __launch_bounds__(v20::kMaxW * 32, 2)
 bimamba_scan_fwd_v20_kernel(const cad_scan_fwd_args a) {
   extern __shared__ unsigned char smem_raw[];
-  v20::kernel_body<T, NPOLY>(a, smem_raw);
-}
-template <typename T>
-static auto v20_kernel_for(int npoly) -> void (*)(const cad_scan_fwd_args) {
-  switch (npoly) {
-    case 1: return bimamba_scan_fwd_v20_kernel<T, 1>;
-    case 2: return bimamba_scan_fwd_v20_kernel<T, 2>;
-    case 3: return bimamba_scan_fwd_v20_kernel<T, 3>;
-    default: return bimamba_scan_fwd_v20_kernel<T, 0>;
-  }
+  v20::kernel_body<T>(a, smem_raw);
 }
 
 int launch_scan_v20(const cad_scan_fwd_args& a, cudaStream_t stream) {
@@ -48,8 +39,7 @@ int launch_scan_v20(const cad_scan_fwd_args& a, cudaStream_t stream) {
   CAD_REQUIRE(W >= 1 && W <= v20::kMaxW, "cad_bimamba_scan_fwd: channels_per_cta (warps per CTA for variant 20) must be in "
               "[1, %d]", v20::kMaxW);
   const size_t smem = v20::smem_bytes(W);
-  const int npoly = a.variant - 20;       // 21..23: that many of the 8 state pairs take their exp2 from the FMA pipe
-  void (*kern)(const cad_scan_fwd_args) = a.io_dtype == CAD_BF16 ? v20_kernel_for<__nv_bfloat16>(npoly) : v20_kernel_for<__half>(npoly);
+  void (*kern)(const cad_scan_fwd_args) = a.io_dtype == CAD_BF16 ? bimamba_scan_fwd_v20_kernel<__nv_bfloat16> : bimamba_scan_fwd_v20_kernel<__half>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(v20): %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)((ngroups + W - 1) / W), (unsigned)a.njobs, (unsigned)nseg);

@@ -21,38 +21,20 @@
 // (grid.z), scan each from a ZERO state (this kernel: outputs, end state and sum dt of every segment) and resolve the carries
 // afterwards exactly like the multi-GPU path does: cad_seg_carry composes the carry-in of every segment,
 // cad_bimamba_scan_fixup adds its decaying contribution in place.  Inference only (no saved chunk states), 16-bit I/O; the
-// sharding hooks are served by the same machinery: conv halo here, carry-in / end state / sum dt by cad_seg_carry.  Written against the SIMT primitives of scan_fwd_v4/v9.cuh so that tests/emu/ compiles THIS file
-// for the host.
+// sharding hooks are served by the same machinery: conv halo here, carry-in / end state / sum dt by cad_seg_carry.  Written
+// against the SIMT primitives of simt.cuh so that tests/emu/ compiles THIS file for the host.
 #pragma once
 #include <type_traits>
 
-#include "scan_fwd_v9.cuh"
+#include "simt.cuh"
 
 namespace cad {
 namespace v20 {
 
-#ifndef CAD_EMULATE
-#define CAD_BIDZ ((int)blockIdx.z)
-// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map)
-CAD_DEV void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-template <int N> CAD_DEV void cp_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-CAD_DEV void stg128f(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
-CAD_DEV uint32_t lds16u(uint32_t addr) {               // one 16-bit element of a staged row (zero-extended)
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-  return v;
-}
-CAD_DEV void sts16u(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory"); }
-CAD_DEV uint32_t f2u(float f) { return __float_as_uint(f); }
-CAD_DEV float u2f(uint32_t u) { return __uint_as_float(u); }
-#endif
-
-using v9::atomic_inc_shared; using v9::sts32u; using v9::warp_sync;
-using v4::fma2; using v4::mul2; using v4::splat; using v4::ex2_2; using v4::lds128u; using v4::cp_async16s;
-using v4::cp_commit; using v4::cta_sync; using v4::stg128; using v4::add2;
+using simt::atomic_inc_shared; using simt::sts32u; using simt::warp_sync; using simt::fma2; using simt::mul2; using simt::add2;
+using simt::splat; using simt::ex2_2; using simt::lds128u; using simt::lds16u; using simt::sts16u; using simt::cp_async16s;
+using simt::cp_commit; using simt::cp_wait_group; using simt::bulk_load_1d; using simt::cta_sync; using simt::stg128;
+using simt::stg128f; using simt::f2u; using simt::u2f;
 
 constexpr int NST = 16;                 // d_state
 constexpr int NPAIR = NST / 2;          // packed state pairs per lane
@@ -64,26 +46,6 @@ constexpr int kStages = 4;              // depth of the per-lane cp.async ring (
 constexpr int kAhead = kStages - 2;     // groups in flight ahead of the one being consumed
 constexpr int kStageBytes = 3 * 32 * 16;           // x, dt_raw, z: 16 bytes per lane each
 constexpr int kMaxW = 8;                // warps per CTA (each 32 channels)
-
-// exp2 of a pair on the FMA pipe instead of the MUFU pipe (the FlashAttention-4 trick), for x <= 0:  round x to the nearest
-// integer n with the 1.5 * 2^23 trick, 2^(x - n) by a degree-5 polynomial with p(0) = 1 exactly (so that a -> 1 as dt*A -> 0:
-// the error of 1 - a stays relative), 2^n by adding n to the exponent field.  Max relative error 1.6e-7 in fp32 Horner form
-// (MUFU ex2.approx: 2 ulp = 2.4e-7).  7 issue slots per value instead of 1 MUFU slot + 8 MUFU-pipe cycles.
-CAD_DEV float2 ex2_poly2(const float2& x) {
-  constexpr float kMagic = 12582912.f;                         // 1.5 * 2^23: low mantissa bits of x + kMagic = round(x)
-  const float2 xc = make_float2(fmaxf(x.x, -126.f), fmaxf(x.y, -126.f));
-  const float2 t = add2(xc, splat(kMagic));
-  const float2 f = fma2(add2(t, splat(-kMagic)), splat(-1.f), xc);          // x - round(x), in [-0.5, 0.5]
-  float2 p = fma2(splat(0.001326472614891827f), f, splat(0.009671512991189957f));
-  p = fma2(p, f, splat(0.05550733581185341f));
-  p = fma2(p, f, splat(0.24022242426872253f));
-  p = fma2(p, f, splat(0.6931470036506653f));
-  p = fma2(p, f, splat(1.0f));
-  return make_float2(u2f(f2u(p.x) + (f2u(t.x) << 23)), u2f(f2u(p.y) + (f2u(t.y) << 23)));
-}
-// pair `p` of the NPAIR state pairs: the last NPOLY pairs (largest |A|: the decays whose error matters least) use the polynomial
-template <int NPOLY>
-CAD_DEV float2 ex2_pair(int p, const float2& x) { return p >= NPAIR - NPOLY ? ex2_poly2(x) : ex2_2(x); }
 
 struct Smem {
   uint32_t tile[2];     // the two B / C chunk buffers
@@ -115,7 +77,7 @@ CAD_DEV void block_range(int64_t L, int nseg, int64_t k, int64_t& lo, int64_t& h
   if (lo > hi) lo = hi;
 }
 
-template <typename T, bool REV, int NPOLY>
+template <typename T, bool REV>
 CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, int seq, int pset) {
   const int lane = CAD_TID & 31, warp = CAD_TID >> 5, W = CAD_NTHREADS >> 5;
   const int64_t L = a.L, E = a.E;
@@ -198,7 +160,6 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
       // a read is 4 wavefronts; reading token PAIRS as words halves that but measured slower (1.42 ms: longer chain per token).
       const uint4 dq = lds128u(stage_s + 512);
       const T* de = reinterpret_cast<const T*>(&dq);
-      const __half* dh = reinterpret_cast<const __half*>(&dq);
       auto el16 = [](uint32_t bits) -> float {
         if constexpr (std::is_same<T, __nv_bfloat16>::value) return u2f(bits << 16);
         else return __half2float(__ushort_as_half((unsigned short)bits));
@@ -209,13 +170,8 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
         else return (uint32_t)__half_as_ushort(__float2half_rn(v));
       };
       float dv[GT];                                            // dt of the group's tokens (physical order)
-      if (a.delta_is_dt) {                                     // launch-uniform: conv_xproj already applied the softplus
 #pragma unroll
-        for (int j = 0; j < GT; ++j) dv[j] = __half2float(dh[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < GT; ++j) dv[j] = softplus(io<T>::to_f(de[j]) + dtb);
-      }
+      for (int j = 0; j < GT; ++j) dv[j] = softplus(io<T>::to_f(de[j]) + dtb);
 #pragma unroll
       for (int i = 0; i < GT; ++i) {
         const int pi = REV ? GT - 1 - i : i;                  // physical position inside the group
@@ -233,8 +189,8 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
 #pragma unroll
         for (int p4 = 0; p4 < NPAIR / 2; ++p4) {               // 4 states per 16-byte piece: two packed pairs
           const float4 bq = lds128(tok + 16 * p4), cq = lds128(tok + NST * 4 + 16 * p4);
-          const float2 a0 = ex2_pair<NPOLY>(2 * p4, mul2(dt2, A2p[2 * p4]));
-          const float2 a1 = ex2_pair<NPOLY>(2 * p4 + 1, mul2(dt2, A2p[2 * p4 + 1]));
+          const float2 a0 = ex2_2(mul2(dt2, A2p[2 * p4]));
+          const float2 a1 = ex2_2(mul2(dt2, A2p[2 * p4 + 1]));
           h2[2 * p4] = fma2(a0, h2[2 * p4], mul2(du2, make_float2(bq.x, bq.y)));
           h2[2 * p4 + 1] = fma2(a1, h2[2 * p4 + 1], mul2(du2, make_float2(bq.z, bq.w)));
           ya = fma2(make_float2(cq.x, cq.y), h2[2 * p4], ya);
@@ -300,7 +256,7 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
   }
 }
 
-template <typename T, int NPOLY>
+template <typename T>
 CAD_DEV void kernel_body(const cad_scan_fwd_args& a, unsigned char* smem_raw) {
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   Smem sm;
@@ -314,8 +270,8 @@ CAD_DEV void kernel_body(const cad_scan_fwd_args& a, unsigned char* smem_raw) {
   cta_sync();
   const int job = CAD_BIDY;
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
-  if (rev) run_segment<T, true, NPOLY>(a, sm, job, seq, pset);
-  else     run_segment<T, false, NPOLY>(a, sm, job, seq, pset);
+  if (rev) run_segment<T, true>(a, sm, job, seq, pset);
+  else     run_segment<T, false>(a, sm, job, seq, pset);
 }
 
 }  // namespace v20

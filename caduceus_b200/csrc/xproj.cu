@@ -5,7 +5,7 @@
 // touches HBM, x is read once, and the kernel writes exactly what the fused scan consumes:
 //     delta (njobs, E, ldd)   = W_dt . x_dbl[0:R]            io dtype (same rounding point as the reference pipeline)
 //     bc    (njobs, 2N, ldbc) = x_dbl[R:R+2N]                fp32, zero beyond the sequence end (TMA tile source)
-//     bc16  (njobs, 2N, ldbc16)  optionally, the same rows in the io dtype (tile source of scan variants 9 / 10)
+//     bcT   (njobs, ldT, 2N)     optionally, the same values token-major (what the lane = channel scan, variant 20, reads)
 // Tensor cores are used for the two dense projections only (north_star): mma.sync m16n8k16 with fp32 accumulation;
 // both GEMMs are skinny (M = R+2N = 48 resp. K = R = 16) and the kernel is HBM-bound on the delta write, so
 // the legacy warp-level MMA path is already far above what the memory system needs (profiles/).
@@ -52,8 +52,6 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
-template <typename T>
-__device__ __forceinline__ float round_io(float v) { return io<T>::to_f(io<T>::from_f(v)); }
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   T v[2] = {io<T>::from_f(lo), io<T>::from_f(hi)};
@@ -245,11 +243,6 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
             if (t < a.ldT) dT[0] = t < L ? v0 : 0.f;
             if (t + 1 < a.ldT) dT[2 * N] = t + 1 < L ? v1 : 0.f;
           }
-          if (a.bc16 && t < a.ldbc16) {        // the same rows in the io dtype: tile source of scan variants 9 / 10
-            T* d16 = static_cast<T*>(a.bc16) + ((int64_t)job * 2 * N + (r - R)) * a.ldbc16 + t;
-            if (t + 1 < a.ldbc16) *reinterpret_cast<uint32_t*>(d16) = pack2<T>(t < L ? v0 : 0.f, t + 1 < L ? v1 : 0.f);
-            else d16[0] = io<T>::from_f(t < L ? v0 : 0.f);
-          }
         }
       }
   __syncthreads();
@@ -264,26 +257,15 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_kernel(cad_conv_xproj_args 
   }
   T* mystg = stg + (size_t)warp * 16 * UP;
   T* __restrict__ dbase = static_cast<T*>(a.delta) + (int64_t)job * E * a.ldd;
-  const bool emit_dt = a.dt_b != nullptr;           // launch-uniform
   for (int64_t mt = warp; mt < E / 16; mt += 8) {
     uint32_t afr[4];
     ldsm_x4(afr, wdts + (16 * mt + (lane & 15)) * DP + 8 * (lane >> 4));
-    float db0 = 0.f, db1 = 0.f;
-    if (emit_dt) { db0 = a.dt_b[(int64_t)pset * E + 16 * mt + g]; db1 = a.dt_b[(int64_t)pset * E + 16 * mt + g + 8]; }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
       mma_t<T>::mma(c, afr, bdt[j]);
-      if (emit_dt) {      // (branch kept inside the loop: the unswitched form costs 12 more registers and spills)
-        // dt = softplus(dt_raw rounded to the io dtype (the reference's rounding point) + bias), stored as fp16
-        *reinterpret_cast<uint32_t*>(mystg + g * UP + 8 * j + q2) =
-            pack2<__half>(softplus(round_io<T>(c[0]) + db0), softplus(round_io<T>(c[1]) + db0));
-        *reinterpret_cast<uint32_t*>(mystg + (g + 8) * UP + 8 * j + q2) =
-            pack2<__half>(softplus(round_io<T>(c[2]) + db1), softplus(round_io<T>(c[3]) + db1));
-      } else {
-        *reinterpret_cast<uint32_t*>(mystg + g * UP + 8 * j + q2) = pack2<T>(c[0], c[1]);
-        *reinterpret_cast<uint32_t*>(mystg + (g + 8) * UP + 8 * j + q2) = pack2<T>(c[2], c[3]);
-      }
+      *reinterpret_cast<uint32_t*>(mystg + g * UP + 8 * j + q2) = pack2<T>(c[0], c[1]);
+      *reinterpret_cast<uint32_t*>(mystg + (g + 8) * UP + 8 * j + q2) = pack2<T>(c[2], c[3]);
     }
     __syncwarp();
 #pragma unroll
@@ -315,8 +297,6 @@ extern "C" int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream_) {
               "cad_conv_xproj_fwd: bad row pitches");
   CAD_REQUIRE(aligned16(a->xz) && aligned16(a->delta) && aligned16(a->w_x) && ((uintptr_t)a->bc & 7) == 0 &&
               a->ldbc % 2 == 0, "cad_conv_xproj_fwd: alignment");
-  CAD_REQUIRE(!a->bc16 || (((uintptr_t)a->bc16 & 3) == 0 && a->ldbc16 % 2 == 0 && a->ldbc16 >= a->L),
-              "cad_conv_xproj_fwd: bc16 must be 4-byte aligned with an even pitch >= L");
   CAD_REQUIRE(!a->bcT || (aligned16(a->bcT) && a->ldT >= a->L), "cad_conv_xproj_fwd: bcT must be 16-byte aligned with ldT >= L");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   static_assert(2 * KC * XP >= 8 * 16 * UP, "output staging must fit in the x slabs it aliases");

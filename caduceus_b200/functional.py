@@ -16,13 +16,9 @@ _DT = {torch.float32: CAD_F32, torch.float16: CAD_F16, torch.bfloat16: CAD_BF16}
 LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py reports the count of a timed region)
 
 # Tuning knobs (module globals so that bench.py / tests can flip them; the environment only sets the initial value).
-# Every value 0 / unset means "library default"; the variants are described at cad_scan_fwd_args.variant /
-# cad_scan_bwd_args.variant in include/caduceus_b200.h and measured in DESIGN.md §4.1.
-SCAN_TOKENS_PER_LANE = 0                                            # 8 / 16: tokens per lane of scan variant 3
-SCAN_VARIANT = int(os.environ.get("CAD_SCAN_VARIANT", "0"))         # forward scan: 3, 4, 7, 9..12, 20..23
-SCAN_NSEG = int(os.environ.get("CAD_SCAN_NSEG", "0"))               # variants 20..23: time segments per job
-SCAN_DT_IN_XPROJ = os.environ.get("CAD_DT_IN_XPROJ", "0") == "1"    # variants 9..12: conv_xproj emits dt = softplus(.) as fp16
-SCAN_BWD_VARIANT = int(os.environ.get("CAD_SCAN_BWD_VARIANT", "0"))  # backward scan: 1, 2
+# The two forward-scan kernels are described at cad_scan_fwd_args.variant in include/caduceus_b200.h and measured in DESIGN.md §4.
+SCAN_VARIANT = int(os.environ.get("CAD_SCAN_VARIANT", "0"))         # 0 = choose per call (choose_scan_variant); 3 / 20 = force
+SCAN_NSEG = int(os.environ.get("CAD_SCAN_NSEG", "0"))               # variant 20: time segments per job (0 = default_nseg)
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
 
@@ -260,12 +256,10 @@ def conv_xproj_supported(xz, N, R):
     return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 1024
 
 
-def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=False, dt_b=None, want_bcT=False):
+def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=False):
     """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores: returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32)
-    without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.  want_bc16: also return the
-    B / C rows in the activation dtype (njobs, 2N, ceil64(L)) — the tile source of scan variants 9 / 10.
-    dt_b (P, E) fp32: `delta` then holds dt = softplus(dt_raw + dt_b) as FP16 bits (scan_fwd(..., delta_is_dt=True)).
-    want_bcT: also return the B / C rows token-major, (njobs, ceil256(L), 2N) fp32 — what scan variants 20..23 read."""
+    without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.
+    want_bcT: also return the B / C rows token-major, (njobs, ceil256(L), 2N) fp32 — what scan variant 20 reads."""
     lib = _lib.load()
     seq, pset, rev = jobs
     nseq, twoE, ld = xz.shape
@@ -276,11 +270,9 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=Fal
     ldbc = round_up(max(L, 1), 32)
     delta = torch.empty(njobs, E, ld, device=xz.device, dtype=xz.dtype)
     bc = torch.empty(njobs, 2 * N, ldbc, device=xz.device, dtype=torch.float32)
-    bc16 = torch.empty(njobs, 2 * N, round_up(max(L, 1), 64), device=xz.device, dtype=xz.dtype) if want_bc16 else None
     a = _lib.ConvXprojArgs(_ptr(xz), _ptr(w_x.contiguous()), _ptr(w_dt.contiguous()), _ptr(conv_w4), _ptr(conv_b),
                            _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(delta), _ptr(bc),
-                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), _ptr(bc16), bc16.stride(1) if want_bc16 else 0,
-                           _ptr(dt_b), None, 0)
+                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), None, 0)
     bcT = None
     if want_bcT:
         Lp, L128 = round_up(max(L, 1), 256), round_up(max(L, 1), 128)
@@ -290,8 +282,7 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bc16=Fal
         a.bcT, a.ldT = _ptr(bcT), Lp
     _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
     _launched()
-    out = (delta, bc, bc16) if want_bc16 else (delta, bc)
-    return out + (bcT,) if want_bcT else out
+    return (delta, bc, bcT) if want_bcT else (delta, bc)
 
 
 def project_dt_bc(xdbl, dt_w_job, L, N):
@@ -307,11 +298,10 @@ def project_dt_bc(xdbl, dt_w_job, L, N):
 
 
 def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=False, want_chunk_state=False,
-             channels_per_cta=0, state_only=False, tokens_per_lane=None, variant=None, bc16=None, delta_is_dt=False,
-             nseg=None, bcT=None):
+             channels_per_cta=0, state_only=False, variant=None, nseg=None, bcT=None):
     """Launch the fused bidirectional scan.
     xz (nseq, 2E, ld), delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32 -> out (njobs, E, ld).
-    nseg: time segments per job for variant 20 (None = SCAN_NSEG / a grid of about two CTAs per SM)."""
+    variant: None = SCAN_VARIANT, else choose_scan_variant(); nseg: time segments per job for variant 20 (None = default_nseg)."""
     lib = _lib.load()
     seq, pset, rev = jobs
     conv_w4, conv_b, dt_b, A2, Dk = packed
@@ -321,6 +311,10 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     P, _, N = A2.shape
     assert twoN == 2 * N and delta.shape[0] == njobs and delta.shape[1] == E
     want_state = want_state or state_only
+    plain = h0 is None and not want_chunk_state and not state_only
+    if variant is None:
+        variant = choose_scan_variant(xz.dtype, N, njobs, E, L) if plain else 3
+    variant = int(variant) or 3
     out = None if state_only else torch.empty(njobs, E, ldxz, device=xz.device, dtype=xz.dtype)
     hlast = torch.empty(njobs, E, N, device=xz.device, dtype=torch.float32) if want_state else None
     dtsum = torch.empty(njobs, E, device=xz.device, dtype=torch.float32) if want_state else None
@@ -331,24 +325,15 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     a = _lib.ScanFwdArgs(
         _ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
-        L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only),
-        SCAN_TOKENS_PER_LANE if tokens_per_lane is None else int(tokens_per_lane), 0, None, 0, int(delta_is_dt))
-    a.variant = scan_variant(a) if variant is None else int(variant)
-    if a.variant in (20, 21, 22, 23):
-        if h0 is not None or want_chunk_state or state_only:
+        L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only), variant)
+    if variant == 20:
+        if not plain:
             raise RuntimeError("scan variant 20 covers inference only (no carry-in at launch, saved chunk states or state-only "
                                "pass; a sequence shard takes its carry-in through scan_fixup(..., seg_ctx=...))")
         # the kernel itself produces neither end state nor sum dt: they are composed from the segment outputs
         a.hlast, a.dtsum = None, None
         return scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=nseg, warps_per_cta=channels_per_cta,
                                   bcT=bcT, want_state=want_state)
-    if a.variant in (9, 10):
-        # 16-bit copy of the B / C rows for the 16-bit-tile kernels (experimental path: a cast per call until the
-        # conv_xproj kernel writes it directly); columns [L, ldbc16) must be zero
-        if bc16 is None:
-            bc16 = torch.zeros(njobs, twoN, round_up(L, 64), device=xz.device, dtype=xz.dtype)
-            bc16[..., :L] = bc[..., :L]
-        a.bc16, a.ldbc16 = _ptr(bc16), bc16.stride(1)
     ev = None
     if SCAN_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -359,6 +344,26 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
         ev[1].record()
         SCAN_EVENTS.append(ev)
     return out, hlast, dtsum, cstate
+
+
+def v20_warps_per_cta(njobs, E):
+    """Warps (32 channels each) per CTA of scan variant 20: fewer when there are few jobs, so that the segments fill two CTAs per SM."""
+    return min(8 if njobs >= 4 else 4 if njobs >= 2 else 2, (E + 31) // 32)
+
+
+def choose_scan_variant(dtype, N, njobs, E, L):
+    """Forward-scan kernel for a plain inference call (no carry-in / saved states): SCAN_VARIANT when forced, else the lane = channel
+    kernel (20) when the call is 16-bit and long enough to give every SM at least eight of its warps with segments of >= 2048
+    tokens (Caduceus-PS and -Ph at 131k on one GPU, halves of it on two), else the time-parallel kernel (3): short sequences and
+    the shards of a 4- or 8-way split have too few (job, channel group, segment) warps for a kernel without time parallelism."""
+    ok20 = dtype in (torch.bfloat16, torch.float16) and N == 16
+    if SCAN_VARIANT:
+        return SCAN_VARIANT if (SCAN_VARIANT != 20 or ok20) else 3
+    if not ok20:
+        return 3
+    sms = _lib.load().cad_sm_count() or 148
+    warps = njobs * ((E + 31) // 32) * default_nseg(njobs, E, L, v20_warps_per_cta(njobs, E))
+    return 20 if warps >= 8 * sms else 3
 
 
 def default_nseg(njobs, E, L, warps_per_cta=8):
@@ -390,8 +395,7 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     E, N, dev = a.E, twoN // 2, xz.device
     if cutoff_log2 is None:
         cutoff_log2 = -16.0 if xz.dtype == torch.bfloat16 else -20.0
-    # warps (32 channels each) per CTA: fewer when there are few jobs, so that about 37 segments per job fill two CTAs per SM
-    W = warps_per_cta if warps_per_cta > 0 else min(8 if njobs >= 4 else 4 if njobs >= 2 else 2, (E + 31) // 32)
+    W = warps_per_cta if warps_per_cta > 0 else v20_warps_per_cta(njobs, E)
     nseg = default_nseg(njobs, E, L, W) if nseg is None else int(nseg)
     Lp = round_up(max(L, 1), 256)
     if bcT is None:                               # conv_xproj(want_bcT=True) writes it directly; otherwise one transpose launch
@@ -419,8 +423,6 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
         carry = torch.empty(njobs, nseg, E, N, device=dev, dtype=torch.float32)
         _lib.check(lib.cad_seg_carry(_ptr(seg_state), _ptr(seg_dtsum), _ptr(A2), _ptr(pset), None, _ptr(carry), None, None,
                                      njobs, nseg, E, _stream()), "cad_seg_carry")
-        if a.delta_is_dt:
-            raise RuntimeError("scan variant 20 with nseg > 1 needs dt_raw (the fix-up kernel applies the softplus itself)")
         f = _lib.ScanFixupArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
                                _ptr(rev), None, L, E, N, a.ldxz, a.ldd, ldbc, a.ldo, a.nseq, njobs, a.io_dtype, 0,
                                float(cutoff_log2), nseg, _ptr(carry))
@@ -431,21 +433,6 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
         SCAN_EVENTS.append(ev)
     seg_ctx = {"nseg": nseg, "seg_state": seg_state, "seg_dtsum": seg_dtsum, "cutoff_log2": cutoff_log2} if want_state else None
     return out, hlast, dtsum, seg_ctx
-
-
-def scan_variant(a):
-    """Kernel variant for a forward-scan call when the caller did not force one: SCAN_VARIANT (env CAD_SCAN_VARIANT)
-    where that variant covers the call (variant 4 is inference-only), else the library default."""
-    if SCAN_VARIANT == 4:
-        ok = (a.io_dtype != CAD_F32 and a.N == 16 and a.E % 2 == 0 and not (a.halo or a.h0 or a.hlast or a.dtsum
-              or a.chunk_state) and not a.state_only and a.tokens_per_lane in (0, 16))
-        return 4 if ok else 0
-    if SCAN_VARIANT in (9, 10, 11, 12):
-        return SCAN_VARIANT if (a.io_dtype != CAD_F32 and a.N == 16 and a.tokens_per_lane in (0, 16)) else 0
-    if SCAN_VARIANT in (20, 21, 22, 23):
-        ok = a.io_dtype != CAD_F32 and a.N == 16 and not (a.h0 or a.chunk_state) and not a.state_only
-        return SCAN_VARIANT if ok else 0
-    return SCAN_VARIANT
 
 
 def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, channels_per_cta=0, seg_ctx=None):
@@ -557,10 +544,9 @@ def conv_halo_grad(xz, du_total, halo, conv_w4, conv_b, jobs, L):
 
 
 def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None, want_dh0=False,
-             channels_per_cta=0, dhlast=None, variant=None):
+             channels_per_cta=0, dhlast=None):
     """Backward of scan_fwd: returns dz, du (scan path), ddelta (io dtype), dbc (fp32), ddt_b, dA2, dD, dh0.
-    `dhlast` (njobs, E, N): gradient w.r.t. the end state, i.e. the adjoint entering from the next shard.
-    `variant`: cad_scan_bwd_args.variant (None = SCAN_BWD_VARIANT / CAD_SCAN_BWD_VARIANT, 0 = library default)."""
+    `dhlast` (njobs, E, N): gradient w.r.t. the end state, i.e. the adjoint entering from the next shard."""
     lib = _lib.load()
     seq, pset, rev = jobs
     conv_w4, conv_b, dt_b, A2, Dk = packed
@@ -585,7 +571,7 @@ def scan_bwd(xz, delta, bc, dout, packed, jobs, L, cstate, *, halo=None, h0=None
         _ptr(dz), _ptr(du), _ptr(ddelta), _ptr(dbc), _ptr(ddt_b), _ptr(dA2), _ptr(dD), _ptr(dh0),
         _ptr(dhlast),
         L, E, N, 4, ldxz, delta.stride(1), ldbc, dout.stride(1), ldxz, ldxz, ldxz,
-        nseq, njobs, P, _dt(xz), channels_per_cta, SCAN_BWD_VARIANT if variant is None else int(variant))
+        nseq, njobs, P, _dt(xz), channels_per_cta)
     _lib.check(lib.cad_bimamba_scan_bwd(C.byref(a), _stream()), "cad_bimamba_scan_bwd")
     _launched()
     return dz, du, ddelta, dbc, ddt_b, dA2, dD, dh0

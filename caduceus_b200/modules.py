@@ -261,23 +261,16 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
         halo = CF.peer_halo_exchange(peer.ctx, xz, L, jobs)
     elif sharded:      # the 3 conv samples that logically precede this shard (one tiny all_gather)
         halo = seqshard.gather_halo(xz[:, :E, :], L, jobs[0], jobs[2], shard).to(act)
+    # forward-scan kernel of this call (CF.choose_scan_variant): the lane = channel kernel (20) reads B / C token-major
+    variant = CF.choose_scan_variant(xz.dtype, N, jobs[0].numel(), E, L)
+    bcT = None
     if CF.conv_xproj_supported(xz, N, m0.dt_rank) and not _FORCE_UNFUSED_XPROJ:
         # one tensor-core kernel: conv+SiLU -> x_proj -> dt_proj; u never touches HBM
-        bc16 = None
-        # softplus(dt_raw + b) in this kernel's epilogue instead of the scan's prologue (variants 9..12, unsharded
-        # inference only: the fix-up kernel of the sharded path and the backward need dt_raw)
-        dt_ready = CF.SCAN_DT_IN_XPROJ and CF.SCAN_VARIANT in (9, 10, 11, 12) and not sharded
-        dt_b = packed[2] if dt_ready else None
-        bcT = None
-        if CF.SCAN_VARIANT in (20, 21, 22, 23) and not sharded:   # lane = channel scan: B / C token-major from the same kernel
+        if variant == 20:
             delta, bc, bcT = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo, want_bcT=True)
-        elif CF.SCAN_VARIANT in (9, 10):     # 16-bit-tile scan variants: the tile source comes straight from this kernel
-            delta, bc, bc16 = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo,
-                                            want_bc16=True, dt_b=dt_b)
         else:
-            delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo, dt_b=dt_b)
+            delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo)
     else:
-        bc16, bcT, dt_ready = None, None, False
         u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                    # (njobs, E, Lp)
         wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)
         xdbl = torch.bmm(wx_job, u)                                                       # (njobs, R+2N, Lp)
@@ -288,12 +281,12 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
 
     # ---- fused scan --------------------------------------------------------------------------------------
     if not sharded:
-        yg = CF.scan_fwd(xz, delta, bc, packed, jobs, L, bc16=bc16, delta_is_dt=dt_ready, bcT=bcT)[0]
+        yg = CF.scan_fwd(xz, delta, bc, packed, jobs, L, variant=variant, bcT=bcT)[0]
     else:
         # zero-carry scan (outputs + end state + sum dt) -> ONE all_gather -> compose this shard's carry-in ->
         # add its decaying contribution in place (seqshard.py, csrc/scan_fixup.cu).  Ranks never wait for each other.
         # (with scan variant 20 the shard is itself cut into segments: seg_ctx carries their end states to the fix-up)
-        yg, hl, ds, seg_ctx = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True, bc16=bc16)
+        yg, hl, ds, seg_ctx = CF.scan_fwd(xz, delta, bc, packed, jobs, L, halo=halo, want_state=True, variant=variant, bcT=bcT)
         if peer is not None:
             h0 = CF.peer_carry_exchange(peer.ctx, hl, ds, packed[3], jobs)
         else:

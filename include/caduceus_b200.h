@@ -144,25 +144,18 @@ typedef struct {
   int32_t io_dtype;         /* dtype of xz / delta / out / halo */
   int32_t channels_per_cta; /* 0 = library picks so that the grid is ~ a multiple of the SM count */
   int32_t state_only;       /* 1: only hlast / dtsum are produced (pass 1 of a sequence-sharded scan); out may be NULL */
-  int32_t tokens_per_lane;  /* 0 = default (16); 8 = 256-token chunks with more CTAs per SM (16-bit I/O, no chunk_state) */
-  int32_t variant;          /* 0 = library default (3); 3 = one channel per warp, scalar fp32 state loop with a replay
-                               pass; 7 = 3 with token pairs packed (FMUL2 / FFMA2) and no replay pass (16 tokens per
-                               lane); 9 / 10 = 7's state loop on a 16-BIT B/C tile (bc16), two tile buffers handed over
-                               through mbarriers + arrival counters instead of a per-chunk CTA barrier, 10 adds the
-                               exp2 software pipeline (16-bit I/O; all hooks); 11 / 12 = the same with an fp32 tile
-                               (bc) shared by up to 14 channels in one CTA per SM; 4 = two channels per warp with packed
-                               fp32 (inference only: 16-bit I/O, even E, no sharding hooks / saved states — an error
-                               otherwise; channels_per_cta then counts channel PAIRS) */
-  const void* bc16;         /* variants 9 / 10 only: (njobs, 2N, ldbc16) B / C rows in the I/O dtype, zeros in [L, ldbc16) */
-  int64_t ldbc16;           /* multiple of 64 elements, >= L */
-  int32_t delta_is_dt;      /* variants 9..12, 16-bit I/O, inference only: `delta` holds dt = softplus(dt_raw + dt_b)
-                               itself as FP16 (whatever io_dtype is), written by cad_conv_xproj_fwd with dt_b set: the
-                               scan's prologue then has no softplus (2 of its MUFU ops per token and channel) */
-  /* variants 20..23 only (lane = channel: a warp owns 32 channels and walks time serially, 16 states per lane as packed pairs,
-     B / C as broadcast reads, no shuffles; 21..23 take the exp2 of 1 / 2 / 3 of the 8 state pairs from a polynomial on the FMA
-     pipe instead of MUFU; channels_per_cta then counts WARPS per CTA, <= 8; 16-bit I/O, inference: no chunk_state /
-     state_only, and h0 / hlast / dtsum go through cad_seg_carry instead of this launch; halo is honoured): */
-  const float* bcT;         /* (njobs, ceil256(L), 2N) fp32: the B / C rows TOKEN-major, zeros beyond L (cad_bc_transpose) */
+  int32_t variant;          /* 0 = library default (3);
+                               3  = one channel per WARP, lane = 16 consecutive tokens of a 512-token chunk: time-parallel inside the
+                                    warp (zero-state pass, 5-step shuffle scan of the segment aggregates, replay).  Every dtype, every
+                                    hook, saved chunk states: the general kernel (training, fp32, short sequences, sequence shards).
+                               20 = one channel per LANE: a warp owns 32 channels and walks time serially, 16 states per lane as packed
+                                    fp32 pairs, B / C as broadcast reads, no shuffles — MUFU-bound (87 % of the pipe).  16-bit I/O,
+                                    inference: no chunk_state / state_only; h0 / hlast / dtsum go through cad_seg_carry instead of this
+                                    launch; halo is honoured; channels_per_cta then counts WARPS per CTA (<= 8).  The sequence is cut
+                                    into nseg segments per job, each scanned from a ZERO state (see below). */
+  /* variant 20 only: */
+  const float* bcT;         /* (njobs, ceil256(L), 2N) fp32: the B / C rows TOKEN-major, zeros beyond L (cad_conv_xproj_fwd writes it,
+                               or cad_bc_transpose) */
   int32_t nseg;             /* time segments per job (grid.z), whole 256-token chunks each; 0 = 1.  Every segment is scanned
                                from a ZERO state: with nseg > 1 `out` still lacks the carries (cad_seg_carry + cad_bimamba_scan_fixup) */
   float* seg_state;         /* (njobs, nseg, E, N) end state of every LOGICAL segment scanned from zero; required when nseg > 1 */
@@ -266,9 +259,6 @@ typedef struct {
   int64_t L, E, N, K;
   int64_t ldxz, ldd, ldbc, ldo, lddz, lddu, lddd;
   int32_t nseq, njobs, npset, io_dtype, channels_per_cta;
-  int32_t variant;          /* 0 = library default (1); 1 = 16 tokens per lane, one 512-token pass per saved chunk
-                               (255 registers, one CTA per SM); 2 = 8 tokens per lane, two 256-token passes per saved
-                               chunk with the midpoint state recomputed (128 registers, two CTAs per SM) */
 } cad_scan_bwd_args;
 int cad_bimamba_scan_bwd(const cad_scan_bwd_args* a, void* stream);
 
@@ -289,8 +279,7 @@ int cad_conv_silu_bwd(const cad_conv_bwd_args* a, void* stream);
  *      cad_bimamba_scan_fwd without materialising u = silu(conv(x)).  Replaces causal_conv1d_fwd + the x_proj and
  *      dt_proj GEMMs of upstream's mamba_inner_fn.
  *        w_x (P, R+2N, E), w_dt (P, E, R) in the io dtype;  delta (njobs, E, ldd) io dtype;
- *        bc (njobs, 2N, ldbc) fp32, written for every column < ldbc (zeros beyond L);
- *        bc16 (njobs, 2N, ldbc16) optional (NULL): the same rows in the io dtype, ldbc16 even, for scan variants 9 / 10.
+ *        bc (njobs, 2N, ldbc) fp32, written for every column < ldbc (zeros beyond L).
  *      Constraints: io dtype f16/bf16, N == 16, R <= 16, E % 64 == 0; otherwise use cad_conv_silu_fwd + GEMMs.   */
 typedef struct {
   const void* xz; const void* w_x; const void* w_dt;
@@ -301,10 +290,7 @@ typedef struct {
   int64_t L, E, N, R;
   int64_t ldxz, ldd, ldbc;
   int32_t nseq, njobs, io_dtype;
-  void* bc16; int64_t ldbc16;
-  const float* dt_b;        /* optional (NULL): (P, E) dt bias; when set, `delta` receives dt = softplus(round_io(dt_raw)
-                               + dt_b) as FP16 instead of dt_raw in the io dtype (cad_scan_fwd_args.delta_is_dt) */
-  float* bcT;               /* optional (NULL): (njobs, ldT, 2N) fp32, the B / C rows TOKEN-major (scan variants 20..23), written for
+  float* bcT;               /* optional (NULL): (njobs, ldT, 2N) fp32, the B / C rows TOKEN-major (scan variant 20), written for
                                tokens [0, min(ldT, ceil128(L))), zeros from L on; the caller zero-fills rows beyond ceil128(L) */
   int64_t ldT;              /* rows per job of bcT (ceil256(L)) */
 } cad_conv_xproj_args;

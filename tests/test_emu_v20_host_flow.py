@@ -1,6 +1,6 @@
 """The HOST orchestration of scan variant 20 (caduceus_b200/functional.py: scan_fwd -> scan_fwd_segmented, scan_fixup with
-seg_ctx) run on CPU: the library handle is replaced by a stand-in whose kernel entry points go to the SIMT emulation of the
-same kernel sources (tests/emu/) and whose two helper entry points are restated in numpy.  What this pins is the Python
+seg_ctx) run on CPU: the library handle is replaced by a stand-in whose scan entry point goes to the SIMT emulation of the
+kernel source (tests/emu/) and whose helper entry points (transpose, carry composition, carry fix-up) are restated in numpy.  What this pins is the Python
 between the kernels — segment count, buffer shapes, argument blocks, the order of the launches, the shard flow
 (want_state -> all_gather stand-in -> scan_fixup(seg_ctx)) — which otherwise runs for the first time on the GPU box.
 TEST INFRASTRUCTURE ONLY: the product path loads the CUDA library and nothing else (tests/test_host.py checks that it fails
@@ -13,7 +13,8 @@ import torch
 
 from caduceus_b200 import _lib, functional as CF
 from scan_boundary_ref import _problem, boundary_ref
-from test_emu_scan_v4 import emu  # noqa: F401  (module-scoped fixture: builds tests/emu/libemu_scan.so)
+from emu_build import emu  # noqa: F401  (module-scoped fixture: builds tests/emu/libemu_scan.so)
+from scan_boundary_ref import _silu, _softplus
 
 N = 16
 
@@ -66,13 +67,43 @@ class _EmuLib:
     def cad_bimamba_scan_fwd(self, ref, stream):
         a = ref._obj
         self.calls.append(f"scan v{a.variant} nseg {a.nseg} W {a.channels_per_cta}")
-        assert a.variant in (20, 21, 22, 23) and not a.h0 and not a.hlast and not a.dtsum and not a.chunk_state
+        assert a.variant == 20 and not a.h0 and not a.hlast and not a.dtsum and not a.chunk_state
         return self.emu.emu_scan_v20(C.byref(a), a.channels_per_cta)
 
     def cad_bimamba_scan_fixup(self, ref, stream):
+        """float64 restatement of the C-ABI contract (include/caduceus_b200.h): out += silu(z) * sum_n C exp2(A2 cumdt) h0, per
+        job (whole shard, carry a.h0) or per (job, logical segment) with the carries of cad_seg_carry.  bf16 I/O."""
         a = ref._obj
         self.calls.append(f"fixup nseg {a.nseg} first {a.seg_first}")
-        return self.emu.emu_scan_fixup(C.byref(a), 7)
+        assert a.io_dtype == _lib.CAD_BF16
+        E, L, nj = a.E, a.L, a.njobs
+        bf = lambda ptr, shape: (_arr(ptr, shape, np.uint16).astype(np.uint32) << 16).view(np.float32)   # noqa: E731
+        xz, delta = bf(a.xz, (a.nseq, 2 * E, a.ldxz)), bf(a.delta, (nj, E, a.ldd))
+        out_raw = _arr(a.out, (nj, E, a.ldo), np.uint16)
+        out = (out_raw.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+        bc = _arr(a.bc, (nj, 2 * N, a.ldbc))
+        seq, ps, rv = (_arr(p, (nj,), np.int32) for p in (a.seq_of_job, a.pset_of_job, a.rev_of_job))
+        P = int(ps.max()) + 1
+        dt_b, A2 = _arr(a.dt_b, (P, E)), _arr(a.A2, (P, E, N))
+        nseg = a.nseg if a.nseg > 1 else 1
+        nch = (L + 255) // 256
+        per = (nch + nseg - 1) // nseg
+        for j in range(nj):
+            for sl in range(0 if (nseg == 1 or a.seg_first) else 1, nseg):
+                k = nseg - 1 - sl if rv[j] else sl
+                lo, hi = min(k * per * 256, L), min((k + 1) * per * 256, L)
+                if hi <= lo:
+                    continue
+                h0 = (_arr(a.seg_carry, (nj, nseg, E, N))[j, sl] if nseg > 1 else _arr(a.h0, (nj, E, N))[j]).astype(np.float64)
+                idx = np.arange(hi - 1, lo - 1, -1) if rv[j] else np.arange(lo, hi)
+                dt = _softplus(delta[j][:, idx].astype(np.float64) + dt_b[ps[j]].astype(np.float64)[:, None])
+                cum = np.cumsum(dt, axis=1)
+                Cm = bc[j, N:][:, idx].astype(np.float64)
+                z = xz[seq[j], E:][:, idx].astype(np.float64)
+                term = np.einsum("nt,ent,en->et", Cm, np.exp2(A2[ps[j]].astype(np.float64)[:, :, None] * cum[:, None, :]), h0)
+                out[j][:, idx] += term * _silu(z)
+        out_raw[:] = torch.from_numpy(out.astype(np.float32)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+        return 0
 
 
 @pytest.fixture()
@@ -120,8 +151,8 @@ def test_host_flow_token_major_copy_supplied_by_conv_xproj(host):
     xz, delta, bc, packed, jobs = _inputs(L, E, spec, 12)
     bcT = torch.zeros(2, 1536, 2 * N)
     bcT[:, :L] = bc[..., :L].transpose(1, 2)
-    out = CF.scan_fwd(xz, delta, bc, packed, jobs, L, variant=22, nseg=2, bcT=bcT.contiguous())[0]
-    assert "transpose" not in host.calls and host.calls[0] == "scan v22 nseg 2 W 1"
+    out = CF.scan_fwd(xz, delta, bc, packed, jobs, L, variant=20, nseg=2, bcT=bcT.contiguous())[0]
+    assert "transpose" not in host.calls and host.calls[0] == "scan v20 nseg 2 W 1"
     _close(out[..., :L].float().numpy(), _ref(xz, delta, bc, packed, spec, L), atol=8e-3)
 
 

@@ -169,39 +169,50 @@ def test_argument_marshalling_and_validation_reach_the_library_without_a_gpu(mon
     monkeypatch.setattr(CF, "_stream", lambda: None)
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(100, 64, [(0, 0, 0)], torch.bfloat16, 0)
     packed = (conv_w4, conv_b, dt_b, A2, Dk)
-    for v in (0, 3, 7, 9, 10, 11, 12, 4):
+    for v in (None, 0, 3):          # 100 tokens: the per-call choice is the time-parallel kernel, too
         with pytest.raises(RuntimeError, match="cad_bimamba_scan_fwd failed .*cuTensorMapEncodeTiled"):
             CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=v)
     with pytest.raises(RuntimeError, match="variant must be"):
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=5)
-    with pytest.raises(RuntimeError, match="variant 4 needs"):
-        CF.scan_fwd(xz.float(), delta.float(), bc, packed, tuple(tabs), 100, variant=4)
-    with pytest.raises(RuntimeError, match="16-bit I/O"):
-        CF.scan_fwd(xz.float(), delta.float(), bc, packed, tuple(tabs), 100, variant=9)
-    with pytest.raises(RuntimeError, match="bc16"):
-        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=9, bc16=torch.zeros(1, 32, 120, dtype=torch.bfloat16))
     cstate = torch.zeros(1, 64, 1, 16)
-    for v in (0, 1, 2):
-        with pytest.raises(RuntimeError, match="cad_bimamba_scan_bwd failed .*cuTensorMapEncodeTiled"):
-            CF.scan_bwd(xz, delta, bc, torch.zeros_like(delta), packed, tuple(tabs), 100, cstate, variant=v)
-    with pytest.raises(RuntimeError, match="unknown variant"):
-        CF.scan_bwd(xz, delta, bc, torch.zeros_like(delta), packed, tuple(tabs), 100, cstate, variant=3)
+    with pytest.raises(RuntimeError, match="cad_bimamba_scan_bwd failed .*cuTensorMapEncodeTiled"):
+        CF.scan_bwd(xz, delta, bc, torch.zeros_like(delta), packed, tuple(tabs), 100, cstate)
     w_x, w_dt = torch.randn(1, 48, 64).bfloat16(), torch.randn(1, 64, 16).bfloat16()
     for want in (False, True):
         with pytest.raises(RuntimeError, match="cad_conv_xproj_fwd failed"):
-            CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, tuple(tabs), 100, want_bc16=want, dt_b=dt_b if want else None)
+            CF.conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, tuple(tabs), 100, want_bcT=want)
     with pytest.raises(RuntimeError, match="cad_bc_transpose failed"):          # variant 20: first launch of its pipeline
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=20, nseg=1)
     with pytest.raises(RuntimeError, match="inference only"):
         CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=20, h0=torch.zeros(1, 64, 16))
-    with pytest.raises(RuntimeError, match="delta_is_dt needs variant 9..12"):
-        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=3, delta_is_dt=True)
-    with pytest.raises(RuntimeError, match="cad_bimamba_scan_fwd failed .*cuTensorMapEncodeTiled"):
-        CF.scan_fwd(xz, delta, bc, packed, tuple(tabs), 100, variant=12, delta_is_dt=True)
+    with pytest.raises(RuntimeError, match="16-bit I/O"):
+        CF.scan_fwd(xz.float(), delta.float(), bc, packed, tuple(tabs), 100, variant=20, nseg=1,
+                    bcT=torch.zeros(1, 256, 32))
+
+
+def test_scan_kernel_choice_per_call():
+    """choose_scan_variant: lane = channel (20) for 16-bit calls with >= 8 warps per SM at >= 2048-token segments, else 3."""
+    from caduceus_b200 import functional as CF
+    bf, f32 = torch.bfloat16, torch.float32
+    assert CF.choose_scan_variant(bf, 16, 4, 512, 131072) == 20        # Caduceus-PS, one GPU
+    assert CF.choose_scan_variant(bf, 16, 2, 512, 131072) == 20        # Caduceus-Ph, one GPU
+    assert CF.choose_scan_variant(bf, 16, 4, 512, 65536) == 20         # PS shard of a 2-way split
+    assert CF.choose_scan_variant(bf, 16, 4, 512, 16384) == 3          # PS shard of an 8-way split: too few warps without time parallelism
+    assert CF.choose_scan_variant(bf, 16, 4, 512, 1024) == 3
+    assert CF.choose_scan_variant(bf, 16, 64, 512, 8192) == 20         # a large batch of medium sequences
+    assert CF.choose_scan_variant(f32, 16, 4, 512, 131072) == 3
+    old = CF.SCAN_VARIANT
+    try:
+        CF.SCAN_VARIANT = 3
+        assert CF.choose_scan_variant(bf, 16, 4, 512, 131072) == 3
+        CF.SCAN_VARIANT = 20
+        assert CF.choose_scan_variant(bf, 16, 4, 512, 1024) == 20 and CF.choose_scan_variant(f32, 16, 4, 512, 1024) == 3
+    finally:
+        CF.SCAN_VARIANT = old
 
 
 def test_segment_count_of_the_lane_per_channel_scan():
-    """variants 20..23: about two CTAs per SM (148 SMs when no device is visible), whole 256-token chunks, no segment shorter
+    """variant 20: about two CTAs per SM (148 SMs when no device is visible), whole 256-token chunks, no segment shorter
     than 2048 tokens; CAD_SCAN_NSEG overrides."""
     from caduceus_b200 import functional as CF
     assert CF.default_nseg(4, 512, 131072, 8) == 37          # Caduceus-PS headline: 4 jobs x 2 channel groups x 37 = 296 CTAs
