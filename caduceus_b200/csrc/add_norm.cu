@@ -50,6 +50,49 @@ __device__ __forceinline__ void store8(void* base, int dtype, int64_t off, const
     *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + off) = raw;
   }
 }
+// The same chunk accessors for rows that are NOT 16-byte addressable (d_model not a multiple of 8 — the reference's 1k-token
+// Caduceus models use d_model = 118 — or odd row pitches): element-wise accesses, `nv` <= 8 valid elements, zeros beyond.
+__device__ __forceinline__ float load1(const void* base, int dtype, int64_t off) {
+  if (dtype == CAD_F32) return __ldg(static_cast<const float*>(base) + off);
+  if (dtype == CAD_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[off]);
+  return __half2float(static_cast<const __half*>(base)[off]);
+}
+__device__ __forceinline__ void store1(void* base, int dtype, int64_t off, float v) {
+  if (dtype == CAD_F32) static_cast<float*>(base)[off] = v;
+  else if (dtype == CAD_BF16) static_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
+  else static_cast<__half*>(base)[off] = __float2half_rn(v);
+}
+template <bool VEC>
+__device__ __forceinline__ void load8g(const void* base, int dtype, int64_t off, int nv, float (&v)[8]) {
+  if constexpr (VEC) { load8(base, dtype, off, v); }
+  else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < nv ? load1(base, dtype, off + k) : 0.f;
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void store8g(void* base, int dtype, int64_t off, int nv, const float (&v)[8]) {
+  if constexpr (VEC) { store8(base, dtype, off, v); }
+  else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < nv) store1(base, dtype, off + k, v[k]);
+  }
+}
+// weight / bias chunk for data columns [c, c + 8): forward order, or read backwards (w'[c + k] = w[D - 1 - c - k])
+template <bool VEC>
+__device__ __forceinline__ void load8w(const void* base, int dtype, int64_t D, int64_t c, int nv, bool flip, float (&w)[8]) {
+  if (!flip) { load8g<VEC>(base, dtype, c, nv, w); return; }
+  if constexpr (VEC) {
+    float t[8];
+    load8(base, dtype, D - 8 - c, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = t[7 - k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = k < nv ? load1(base, dtype, D - 1 - c - k) : 0.f;
+  }
+}
 // round v through dtype (what the stored value will read back as)
 __device__ __forceinline__ float round_to(float v, int dtype) {
   if (dtype == CAD_BF16) return __bfloat162float(__float2bfloat16_rn(v));
@@ -62,8 +105,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// ITER = 8-element chunks per lane; D <= 256 * ITER.
-template <int ITER>
+// ITER = 8-element chunks per lane; D <= 256 * ITER.  VEC: 128-bit accesses (D, pitches multiples of 8, 16-byte aligned bases).
+template <int ITER, bool VEC>
 __global__ void __launch_bounds__(256) add_norm_fwd_kernel(cad_add_norm_args a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -84,14 +127,15 @@ __global__ void __launch_bounds__(256) add_norm_fwd_kernel(cad_add_norm_args a) 
     for (int i = 0; i < ITER; ++i) {
       const int64_t c = (int64_t)(i * 32 + lane) * 8;
       if (c < D) {
-        load8(a.x, a.xdtype, r * a.ldx + hin * D + c, v[i]);
+        const int nv = VEC ? 8 : (int)min((int64_t)8, D - c);
+        load8g<VEC>(a.x, a.xdtype, r * a.ldx + hin * D + c, nv, v[i]);
         if (a.residual) {
           float rr[8];
-          load8(a.residual, a.res_in_dtype, r * a.ldr + hin * D + c, rr);
+          load8g<VEC>(a.residual, a.res_in_dtype, r * a.ldr + hin * D + c, nv, rr);
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[i][k] += rr[k];
         }
-        if (a.res_out) store8(a.res_out, a.res_out_dtype, r * a.ldo + h * D + c, v[i]);
+        if (a.res_out) store8g<VEC>(a.res_out, a.res_out_dtype, r * a.ldo + h * D + c, nv, v[i]);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { s1 += v[i][k]; s2 += v[i][k] * v[i][k]; }
       } else {
@@ -111,8 +155,10 @@ __global__ void __launch_bounds__(256) add_norm_fwd_kernel(cad_add_norm_args a) 
       for (int i = 0; i < ITER; ++i) {
         const int64_t c = (int64_t)(i * 32 + lane) * 8;
         if (c < D) {
+          const int nv = VEC ? 8 : (int)min((int64_t)8, D - c);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { float d = v[i][k] - mean; q += d * d; }
+          for (int k = 0; k < 8; ++k)
+            if (k < nv) { float d = v[i][k] - mean; q += d * d; }
         }
       }
       q = warp_sum(q);
@@ -126,30 +172,18 @@ __global__ void __launch_bounds__(256) add_norm_fwd_kernel(cad_add_norm_args a) 
     for (int i = 0; i < ITER; ++i) {
       const int64_t c = (int64_t)(i * 32 + lane) * 8;
       if (c < D) {
+        const int nv = VEC ? 8 : (int)min((int64_t)8, D - c);
         float w[8], y[8];
-        if (!wflip) {
-          load8(a.weight, a.wdtype, c, w);
-        } else {
-          float t[8];
-          load8(a.weight, a.wdtype, D - 8 - c, t);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) w[k] = t[7 - k];
-        }
+        load8w<VEC>(a.weight, a.wdtype, D, c, nv, wflip, w);
 #pragma unroll
         for (int k = 0; k < 8; ++k) y[k] = (v[i][k] - mean) * rstd * w[k];
         if (a.bias) {
           float b[8];
-          if (!wflip) {
-            load8(a.bias, a.wdtype, c, b);
+          load8w<VEC>(a.bias, a.wdtype, D, c, nv, wflip, b);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) y[k] += b[k];
-          } else {
-            load8(a.bias, a.wdtype, D - 8 - c, b);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) y[k] += b[7 - k];
-          }
+          for (int k = 0; k < 8; ++k) y[k] += b[k];
         }
-        store8(a.y, a.xdtype, r * a.ldy + h * D + c, y);
+        store8g<VEC>(a.y, a.xdtype, r * a.ldy + h * D + c, nv, y);
       }
     }
   }
@@ -162,7 +196,7 @@ __global__ void __launch_bounds__(256) add_norm_fwd_kernel(cad_add_norm_args a) 
 // dv of output half h is the gradient of INPUT half hin = h ^ swap (x and residual share it).
 // Weight/bias gradients are accumulated per block into (nblocks, D) partials (row-serial inside a warp, then
 // a shared-memory reduction over the block's warps) and summed by the caller: deterministic, no atomics.
-template <int ITER>
+template <int ITER, bool VEC>
 __global__ void __launch_bounds__(256) add_norm_bwd_kernel(cad_add_norm_bwd_args a) {
   extern __shared__ float red[];    // (warps, D) for dweight, then (warps, D) for dbias
   const int lane = threadIdx.x & 31;
@@ -193,25 +227,20 @@ __global__ void __launch_bounds__(256) add_norm_bwd_kernel(cad_add_norm_bwd_args
     for (int i = 0; i < ITER; ++i) {
       const int64_t c = (int64_t)(i * 32 + lane) * 8;
       if (c < D) {
+        const int nv = VEC ? 8 : (int)min((int64_t)8, D - c);
         float dy[8], v[8], w[8];
-        load8(a.dy, a.dydtype, r * a.lddy + h * D + c, dy);
-        load8(a.v, a.vdtype, r * a.ldv + h * D + c, v);
-        if (!wflip) {
-          load8(a.weight, a.wdtype, c, w);
-        } else {
-          float t[8];
-          load8(a.weight, a.wdtype, D - 8 - c, t);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) w[k] = t[7 - k];
-        }
+        load8g<VEC>(a.dy, a.dydtype, r * a.lddy + h * D + c, nv, dy);
+        load8g<VEC>(a.v, a.vdtype, r * a.ldv + h * D + c, nv, v);
+        load8w<VEC>(a.weight, a.wdtype, D, c, nv, wflip, w);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          xh[i][k] = (v[k] - mean) * rstd;
+          xh[i][k] = k < nv ? (v[k] - mean) * rstd : 0.f;
           g[i][k] = dy[k] * w[k];
           s_g += g[i][k];
           s_gx += g[i][k] * xh[i][k];
-          // weight-gradient slots are indexed by the UNFLIPPED weight position
-          const int kk = wflip ? 7 - k : k;
+          // weight-gradient slots are indexed by the UNFLIPPED weight position (vector form: mirrored inside the chunk here and
+          // chunk-wise below; scalar form: by data column here, mirrored element-wise below)
+          const int kk = (VEC && wflip) ? 7 - k : k;
           dw[i][kk] += dy[k] * xh[i][k];
           db[i][kk] += dy[k];
         }
@@ -229,13 +258,14 @@ __global__ void __launch_bounds__(256) add_norm_bwd_kernel(cad_add_norm_bwd_args
         float dv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) dv[k] = rstd * (g[i][k] - s_g - xh[i][k] * s_gx);
+        const int nv = VEC ? 8 : (int)min((int64_t)8, D - c);
         if (a.dres_out) {
           float dr[8];
-          load8(a.dres_out, a.drdtype, r * a.lddr + h * D + c, dr);
+          load8g<VEC>(a.dres_out, a.drdtype, r * a.lddr + h * D + c, nv, dr);
 #pragma unroll
           for (int k = 0; k < 8; ++k) dv[k] += dr[k];
         }
-        store8(a.dx, a.dxdtype, r * a.lddx + hin * D + c, dv);
+        store8g<VEC>(a.dx, a.dxdtype, r * a.lddx + hin * D + c, nv, dv);
       }
     }
   }
@@ -256,9 +286,18 @@ __global__ void __launch_bounds__(256) add_norm_bwd_kernel(cad_add_norm_bwd_args
   for (int i = 0; i < ITER; ++i) {
     const int64_t c = (int64_t)(i * 32 + lane) * 8;
     if (c < D) {
-      const int64_t cc = wflip_w ? D - 8 - c : c;
+      if constexpr (VEC) {
+        const int64_t cc = wflip_w ? D - 8 - c : c;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { rw[(int64_t)wib * D + cc + k] = dw[i][k]; rb[(int64_t)wib * D + cc + k] = db[i][k]; }
+        for (int k = 0; k < 8; ++k) { rw[(int64_t)wib * D + cc + k] = dw[i][k]; rb[(int64_t)wib * D + cc + k] = db[i][k]; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c + k < D) {
+            const int64_t col = wflip_w ? D - 1 - c - k : c + k;
+            rw[(int64_t)wib * D + col] = dw[i][k]; rb[(int64_t)wib * D + col] = db[i][k];
+          }
+      }
     }
   }
   __syncthreads();
@@ -287,21 +326,24 @@ extern "C" int cad_add_norm_fwd(const cad_add_norm_args* a, void* stream_) {
   if (a->rows == 0) return 0;
   CAD_REQUIRE(a->x && a->weight && a->y, "cad_add_norm_fwd: null pointer");
   CAD_REQUIRE(a->nhalf == 1 || a->nhalf == 2, "cad_add_norm_fwd: nhalf must be 1 or 2");
-  CAD_REQUIRE(a->D > 0 && a->D % 8 == 0 && a->D <= 2048, "cad_add_norm_fwd: D (%lld) must be a multiple of 8, <= 2048",
-              (long long)a->D);
-  CAD_REQUIRE(a->ldx % 8 == 0 && a->ldy % 8 == 0 && (!a->residual || a->ldr % 8 == 0) &&
-              (!a->res_out || a->ldo % 8 == 0), "cad_add_norm_fwd: row pitches must be multiples of 8 elements");
-  CAD_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->weight) && aligned16(a->residual) &&
-              aligned16(a->res_out) && aligned16(a->bias), "cad_add_norm_fwd: pointers must be 16B aligned");
+  CAD_REQUIRE(a->D > 0 && a->D <= 2048, "cad_add_norm_fwd: D (%lld) must be in [1, 2048]", (long long)a->D);
+  // 128-bit accesses need D and every row pitch to be multiples of 8 elements and 16-byte aligned bases; anything else
+  // (d_model = 118 of the reference's 1k-token models) takes the element-wise instantiation of the same kernel
+  const bool vec = a->D % 8 == 0 && a->ldx % 8 == 0 && a->ldy % 8 == 0 && (!a->residual || a->ldr % 8 == 0) &&
+                   (!a->res_out || a->ldo % 8 == 0) && aligned16(a->x) && aligned16(a->y) && aligned16(a->weight) &&
+                   aligned16(a->residual) && aligned16(a->res_out) && aligned16(a->bias);
   CAD_REQUIRE(a->swap == 0 || a->nhalf == 2, "cad_add_norm_fwd: swap needs nhalf == 2");
   if (a->rows == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int threads = 256;
   const int blocks = norm_grid(a->rows * a->nhalf, threads);
-  if (a->D <= 256) add_norm_fwd_kernel<1><<<blocks, threads, 0, stream>>>(*a);
-  else if (a->D <= 512) add_norm_fwd_kernel<2><<<blocks, threads, 0, stream>>>(*a);
-  else if (a->D <= 1024) add_norm_fwd_kernel<4><<<blocks, threads, 0, stream>>>(*a);
-  else add_norm_fwd_kernel<8><<<blocks, threads, 0, stream>>>(*a);
+#define CAD_NORM_FWD(ITER) do { if (vec) add_norm_fwd_kernel<ITER, true><<<blocks, threads, 0, stream>>>(*a); \
+                               else add_norm_fwd_kernel<ITER, false><<<blocks, threads, 0, stream>>>(*a); } while (0)
+  if (a->D <= 256) CAD_NORM_FWD(1);
+  else if (a->D <= 512) CAD_NORM_FWD(2);
+  else if (a->D <= 1024) CAD_NORM_FWD(4);
+  else CAD_NORM_FWD(8);
+#undef CAD_NORM_FWD
   CAD_LAUNCH_CHECK();
   return 0;
 }
@@ -320,16 +362,19 @@ extern "C" int cad_add_norm_bwd(const cad_add_norm_bwd_args* a, void* stream_) {
   CAD_REQUIRE(a->is_rms || a->mean, "cad_add_norm_bwd: LayerNorm needs the saved mean");
   CAD_REQUIRE(!a->has_bias || a->dbias_partial, "cad_add_norm_bwd: bias gradient buffer missing");
   CAD_REQUIRE(a->nhalf == 1 || a->nhalf == 2, "cad_add_norm_bwd: nhalf must be 1 or 2");
-  CAD_REQUIRE(a->D > 0 && a->D % 8 == 0 && a->D <= 1024, "cad_add_norm_bwd: D must be a multiple of 8, <= 1024");
-  CAD_REQUIRE(a->lddy % 8 == 0 && a->ldv % 8 == 0 && a->lddx % 8 == 0 && (!a->dres_out || a->lddr % 8 == 0),
-              "cad_add_norm_bwd: row pitches must be multiples of 8 elements");
+  CAD_REQUIRE(a->D > 0 && a->D <= 1024, "cad_add_norm_bwd: D (%lld) must be in [1, 1024]", (long long)a->D);
+  const bool vec = a->D % 8 == 0 && a->lddy % 8 == 0 && a->ldv % 8 == 0 && a->lddx % 8 == 0 && (!a->dres_out || a->lddr % 8 == 0) &&
+                   aligned16(a->dy) && aligned16(a->v) && aligned16(a->dx) && aligned16(a->weight) && aligned16(a->dres_out);
   CAD_REQUIRE(a->nblocks >= 1, "cad_add_norm_bwd: nblocks");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int threads = 256;   // 8 warps: even, so with nhalf == 2 every warp sees one half only
   const size_t smem = (size_t)2 * (threads / 32) * a->D * sizeof(float);
-  if (a->D <= 256) add_norm_bwd_kernel<1><<<a->nblocks, threads, smem, stream>>>(*a);
-  else if (a->D <= 512) add_norm_bwd_kernel<2><<<a->nblocks, threads, smem, stream>>>(*a);
-  else add_norm_bwd_kernel<4><<<a->nblocks, threads, smem, stream>>>(*a);
+#define CAD_NORM_BWD(ITER) do { if (vec) add_norm_bwd_kernel<ITER, true><<<a->nblocks, threads, smem, stream>>>(*a); \
+                               else add_norm_bwd_kernel<ITER, false><<<a->nblocks, threads, smem, stream>>>(*a); } while (0)
+  if (a->D <= 256) CAD_NORM_BWD(1);
+  else if (a->D <= 512) CAD_NORM_BWD(2);
+  else CAD_NORM_BWD(4);
+#undef CAD_NORM_BWD
   CAD_LAUNCH_CHECK();
   return 0;
 }

@@ -34,7 +34,7 @@ namespace v20 {
 using simt::atomic_inc_shared; using simt::sts32u; using simt::warp_sync; using simt::fma2; using simt::mul2; using simt::add2;
 using simt::splat; using simt::ex2_2; using simt::lds128u; using simt::lds16u; using simt::sts16u; using simt::cp_async16s;
 using simt::cp_commit; using simt::cp_wait_group; using simt::bulk_load_1d; using simt::cta_sync; using simt::stg128;
-using simt::stg128f; using simt::f2u; using simt::u2f;
+using simt::stg128f; using simt::f2u; using simt::u2f; using simt::warp_all;
 
 constexpr int NST = 16;                 // d_state
 constexpr int NPAIR = NST / 2;          // packed state pairs per lane
@@ -169,9 +169,35 @@ CAD_DEV void run_segment(const cad_scan_fwd_args& a, const Smem& sm, int job, in
         if constexpr (std::is_same<T, __nv_bfloat16>::value) return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
         else return (uint32_t)__half_as_ushort(__float2half_rn(v));
       };
-      float dv[GT];                                            // dt of the group's tokens (physical order)
+      // dt = softplus(dt_raw + b) of the group's tokens (physical order): w = e^v by MUFU for all eight, then log1p(w).  When every
+      // lane of the warp has all eight w below 1/8 (dt < 0.118: the whole init-time range of Mamba's dt) the log comes from the
+      // alternating series on the FMA pipe (7 terms, truncation < 6e-8 relative) instead of a second MUFU op — one of the 20 MUFU
+      // ops per token and channel of this MUFU-bound kernel; otherwise common.cuh's form (lg2, series below 2^-6, threshold 20).
+      float dv[GT];
+      bool small = true;
 #pragma unroll
-      for (int j = 0; j < GT; ++j) dv[j] = softplus(io<T>::to_f(de[j]) + dtb);
+      for (int j = 0; j < GT; ++j) {
+        dv[j] = io<T>::to_f(de[j]) + dtb;
+        const float w = ex2(kLog2e * dv[j]);
+        small = small && (w < 0.125f);
+        dv[j] = small ? w : dv[j];                            // keep w while the fast path is still possible
+      }
+      if (warp_all(small)) {
+#pragma unroll
+        for (int j = 0; j < GT; ++j) {
+          const float w = dv[j];
+          float p = fmaf(w, 0.14285715f, -0.16666667f);
+          p = fmaf(p, w, 0.2f);
+          p = fmaf(p, w, -0.25f);
+          p = fmaf(p, w, 0.33333334f);
+          p = fmaf(p, w, -0.5f);
+          p = fmaf(p, w, 1.0f);
+          dv[j] = w * p;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < GT; ++j) dv[j] = softplus(io<T>::to_f(de[j]) + dtb);
+      }
 #pragma unroll
       for (int i = 0; i < GT; ++i) {
         const int pi = REV ? GT - 1 - i : i;                  // physical position inside the group

@@ -66,6 +66,7 @@ CAD_DEV void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, u
 }
 CAD_DEV void cta_sync() { __syncthreads(); }
 CAD_DEV void warp_sync() { __syncwarp(); }
+CAD_DEV bool warp_all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
 CAD_DEV void stg128(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 CAD_DEV void stg128f(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 CAD_DEV uint32_t f2u(float f) { return __float_as_uint(f); }

@@ -131,7 +131,8 @@ class _AddNormFn(torch.autograd.Function):
         if b is not None and b.dtype != w.dtype:
             b = b.to(w.dtype)
         needs_grad = any(ctx.needs_input_grad[:4])
-        res_dtype = torch.float32 if residual_in_fp32 else x.dtype
+        # upstream keeps the dtype of a residual that is passed in; residual_in_fp32 only decides the dtype of a NEW residual stream
+        res_dtype = residual.dtype if residual is not None else (torch.float32 if residual_in_fp32 else x.dtype)
         y = torch.empty(shape, device=x.device, dtype=x.dtype)
         # the pre-norm sum is written when the caller wants it, or (training) to feed the backward
         store_res = want_res or needs_grad
@@ -353,7 +354,7 @@ def v20_warps_per_cta(njobs, E):
 
 def choose_scan_variant(dtype, N, njobs, E, L):
     """Forward-scan kernel for a plain inference call (no carry-in / saved states): SCAN_VARIANT when forced, else the lane = channel
-    kernel (20) when the call is 16-bit and long enough to give every SM at least eight of its warps with segments of >= 2048
+    kernel (20) when the call is 16-bit and long enough to give every SM at least six of its warps with segments of >= 2048
     tokens (Caduceus-PS and -Ph at 131k on one GPU, halves of it on two), else the time-parallel kernel (3): short sequences and
     the shards of a 4- or 8-way split have too few (job, channel group, segment) warps for a kernel without time parallelism."""
     ok20 = dtype in (torch.bfloat16, torch.float16) and N == 16
@@ -363,17 +364,17 @@ def choose_scan_variant(dtype, N, njobs, E, L):
         return 3
     sms = _lib.load().cad_sm_count() or 148
     warps = njobs * ((E + 31) // 32) * default_nseg(njobs, E, L, v20_warps_per_cta(njobs, E))
-    return 20 if warps >= 8 * sms else 3
+    return 20 if warps >= 6 * sms else 3
 
 
 def default_nseg(njobs, E, L, warps_per_cta=8):
-    """Segments per job for scan variant 20: enough (job, segment, channel-group) CTAs for two per SM, segments of whole
-    256-token chunks and never shorter than 2048 tokens (each segment boundary costs a carry fix-up)."""
+    """Segments per job for scan variant 20: enough (job, channel group, segment) WARPS for eight per SM — measured optimum on the
+    Caduceus-PS / -Ph headline shapes (profiles/r2_call6.log: PS 18 segments 1.87 ms vs 37 segments 1.99 ms; every segment boundary
+    costs a carry fix-up, fewer warps cost MUFU occupancy in the scan) — in whole 256-token chunks and never shorter than 2048 tokens."""
     if SCAN_NSEG > 0:
         return SCAN_NSEG
     sms = _lib.load().cad_sm_count() or 148
-    groups = -(-((E + 31) // 32) // max(1, warps_per_cta))
-    want = max(1, (2 * sms) // max(1, njobs * groups))
+    want = max(1, (8 * sms) // max(1, njobs * ((E + 31) // 32)))
     return max(1, min(want, L // 2048))
 
 

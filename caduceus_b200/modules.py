@@ -149,19 +149,18 @@ def pack_scan_params(dirs):
 
 
 class _DerivedCache:
-    """Inference-time cache of derived weights (flips / stacks / casts), invalidated by parameter versions."""
-
-    def __init__(self):
-        self.store = {}
+    """Inference-time cache of derived weights (flips / stacks / casts), invalidated by parameter versions.  The entries live ON
+    the owning module (`owner._cad_derived`), so they die with the model: no process-wide table, no stale hit through a recycled
+    id() or data_ptr()."""
 
     def get(self, owner, params, tag, build):
-        key = (id(owner), tag)
+        store = owner.__dict__.setdefault("_cad_derived", {})
         sig = tuple((p.data_ptr(), p._version, p.dtype) for p in params if p is not None)
-        hit = self.store.get(key)
+        hit = store.get(tag)
         if hit is not None and hit[0] == sig:
             return hit[1]
         val = build()
-        self.store[key] = (sig, val)
+        store[tag] = (sig, val)
         return val
 
 

@@ -21,6 +21,7 @@ sys.path.insert(0, HERE)
 from ref_loader import load_reference  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+ONLY_D118 = "--only-d118" in sys.argv        # add the d_model = 118 fixtures without rewriting the others
 
 SSM_CFG = dict(d_state=16, d_conv=4, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1, dt_init="random",
                dt_scale=1.0, dt_init_floor=1e-4, conv_bias=True, bias=False, use_fast_path=True)
@@ -152,6 +153,13 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     mc = sys.modules["ref_caduceus.modeling_caduceus"]
+
+    # d_model = 118: the reference's published 1k-token Caduceus-Ph / -PS models (6 slurm scripts of the reference use it) — not a
+    # multiple of the 8-element vector width, so the embedding and add+norm kernels take their element-wise instantiation
+    make_model_fixture(ref, "ps_d118", d_model=118, n_layer=2, seqlen=300, bsz=1, rcps=True, fused_add_norm=True, seed=9)
+    make_model_fixture(ref, "ph_d118", d_model=118, n_layer=2, seqlen=300, bsz=2, rcps=False, fused_add_norm=True, seed=13)
+    if ONLY_D118:
+        return
 
     # BASELINE.json configs[0]: D=128, n_layer=4, L=1024, B=1 MLM forward on the CPU reference path
     make_model_fixture(ref, "ph_config0", d_model=128, n_layer=4, seqlen=1024, bsz=1, rcps=False,

@@ -17,7 +17,8 @@ def _add_norm(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms)
     r = x.float()
     if residual is not None:
         r = r + residual.float()
-    res_dtype = torch.float32 if residual_in_fp32 else out_dtype
+    # upstream: residual_out keeps residual.dtype when a residual is given; residual_in_fp32 only matters for the first block
+    res_dtype = residual.dtype if residual is not None else (torch.float32 if residual_in_fp32 else out_dtype)
     # upstream's one-pass kernel stores the sum in res_dtype but normalises the UNROUNDED fp32 sum
     residual_out = r.to(res_dtype)
     if is_rms:

@@ -25,6 +25,8 @@ static void run_cta(size_t smem_bytes, int G, int bx, int by, Body body, int bz 
   pthread_barrier_init(&cta.cta_bar, nullptr, cta.nthreads);
   cta.warp_bar.resize(G);
   for (int w = 0; w < G; ++w) pthread_barrier_init(&cta.warp_bar[w], nullptr, 32);
+  cta.vote = std::vector<std::atomic<int>>(2 * G);
+  for (auto& v : cta.vote) v.store(0);
   std::vector<std::thread> th;
   for (int t = 0; t < cta.nthreads; ++t)
     th.emplace_back([&, t] {

@@ -54,13 +54,14 @@ struct EmuCta {
   int nthreads = 0;
   pthread_barrier_t cta_bar;
   std::vector<pthread_barrier_t> warp_bar;
+  std::vector<std::atomic<int>> vote;      // [warps][2]: warp_all flags, used alternately
   std::mutex m;
   std::condition_variable cv;
   std::map<const void*, Mbar> mbars;
   bool deadlock = false;
 };
 
-struct EmuThread { EmuCta* cta; int tid, bx, by, bz = 0; };
+struct EmuThread { EmuCta* cta; int tid, bx, by, bz = 0; int vote_epoch = 0; };
 extern thread_local EmuThread g_t;
 
 namespace simt {
@@ -159,6 +160,17 @@ inline void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, ui
 }
 inline void cta_sync() { pthread_barrier_wait(&g_t.cta->cta_bar); }
 inline void warp_sync() { pthread_barrier_wait(&g_t.cta->warp_bar[g_t.tid >> 5]); }
+// __all_sync: two flags per warp used alternately; lane 0 clears the one just read before it can reach the call after next
+inline bool warp_all(bool p) {
+  EmuCta* c = g_t.cta;
+  const int w = g_t.tid >> 5, e = g_t.vote_epoch++ & 1;
+  if (!p) c->vote[2 * w + e].store(1);
+  pthread_barrier_wait(&c->warp_bar[w]);
+  const bool r = c->vote[2 * w + e].load() == 0;
+  pthread_barrier_wait(&c->warp_bar[w]);
+  if ((g_t.tid & 31) == 0) c->vote[2 * w + e].store(0);
+  return r;
+}
 inline void stg128(void* p, const uint4& v) {
   if ((uintptr_t)p & 15) { fprintf(stderr, "emu: misaligned 16-byte global store\n"); abort(); }
   memcpy(p, &v, 16);

@@ -46,8 +46,11 @@ def _apply_carries(out0, seg_state, seg_dtsum, xz, delta, bc, dt_b, A2, spec, L,
     return out
 
 
-def _run(lib, L, E, spec, dtype, W, seed, nseg):
+def _run(lib, L, E, spec, dtype, W, seed, nseg, small_dt=False):
     xz, delta, bc, conv_w4, conv_b, dt_b, A2, Dk, tabs, ld, ldbc = _problem(L, E, spec, dtype, seed)
+    if small_dt:            # every dt below 0.118: the warp-uniform series form of the softplus (no lg2) is taken
+        delta = (delta.float() * 0.05).to(dtype)
+        dt_b[:, 0] = dt_b[:, 1]
     njobs = len(spec)
     delta_f = delta.float()
     Lp = (L + CH - 1) // CH * CH
@@ -129,3 +132,9 @@ def test_emulated_v20_halo_with_fewer_than_three_masked_tail_tokens(emu, L):   #
 
 def test_emulated_v20_many_chunks(emu):   # noqa: F811
     _run(emu, 2300, E=64, spec=[(0, 0, 0), (0, 1, 1)], dtype=torch.bfloat16, W=1, seed=5, nseg=2)
+
+
+@pytest.mark.parametrize("rev", [0, 1])
+def test_emulated_v20_softplus_series_path(emu, rev):   # noqa: F811
+    """init-time dt range in every lane of every warp: dt comes from the log1p series instead of lg2."""
+    _run(emu, 1100, E=64, spec=[(0, 0, rev), (0, 1, 1 - rev)], dtype=torch.bfloat16, W=2, seed=91, nseg=2, small_dt=True)

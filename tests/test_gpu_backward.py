@@ -55,7 +55,7 @@ def test_mixer_backward_vs_oracle_autograd(tag, L):
         _grad_close(p.grad, ref.reshape(p.shape), 5e-3, 2e-3, f"d {name}")
 
 
-@pytest.mark.parametrize("tag", ["ps_small", "ph_small", "ps_nonfused", "ph_nonfused_ln", "ps_ln_fp32res"])
+@pytest.mark.parametrize("tag", ["ps_small", "ph_small", "ps_nonfused", "ph_nonfused_ln", "ps_ln_fp32res", "ps_d118", "ph_d118"])
 def test_model_loss_backward_vs_oracle_autograd(tag):
     """CaduceusForMaskedLM: MLM cross-entropy loss and ALL parameter gradients vs autograd through the oracle."""
     import caduceus
@@ -124,3 +124,27 @@ def test_bf16_autocast_train_step_reduces_loss():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+@pytest.mark.parametrize("rcps", [False, True])
+@pytest.mark.parametrize("D,V", [(512, 16), (1024, 16), (118, 16), (64, 4096)])
+def test_embedding_backward_any_width_and_vocabulary(D, V, rcps):
+    """dW of the (RC-equivariant) embedding for widths beyond one 48 KB tile (d_model 512 / 1024 with the padded vocabulary of 16
+    used to fail at the first backward), a width that is not a multiple of the vector size, and a large vocabulary — against
+    autograd through the literal reference formula (ref:caduceus/modeling_rcps.py:54-67)."""
+    from caduceus_b200 import functional as CF
+    g = torch.Generator().manual_seed(D + V)
+    W = torch.randn(V, D, generator=g).to("cuda").requires_grad_(True)
+    ids = torch.randint(0, V, (3, 257), generator=g).to("cuda")
+    cmap = torch.randperm(V, generator=g).to("cuda") if rcps else None
+    out = CF.embedding(ids, W, cmap)
+    gout = torch.randn(out.shape, generator=g).to("cuda")
+    (dW,) = torch.autograd.grad(out, W, gout)
+    Wr = W.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.embedding(ids, Wr)
+    if rcps:
+        rc = torch.flip(torch.nn.functional.embedding(cmap[torch.flip(ids, dims=[-1])], Wr), dims=[-2, -1])
+        ref = torch.cat([ref, rc], dim=-1)
+    assert torch.equal(out, ref)                      # index work: bit-exact
+    (dWr,) = torch.autograd.grad(ref, Wr, gout)
+    assert torch.allclose(dW, dWr, rtol=1e-5, atol=1e-4), (dW - dWr).abs().max()

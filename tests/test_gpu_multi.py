@@ -88,8 +88,19 @@ def test_peer_exchange_kernels_virtual_ranks(world, dtype):
 @pytest.mark.parametrize("tag,world", [("ps_small", 2), ("ph_small", 3), ("ps_small", 4)])
 def test_sequence_sharded_forward_virtual_ranks(tag, world):
     """The whole model, `world` shards of one batch, one THREAD + stream per virtual rank, halo / boundary states through the
-    peer-exchange kernels: concatenated logits == unsharded forward.  Three forwards in a row (epochs, both buffer parities)."""
-    from caduceus_b200 import functional as CF, seqshard
+    peer-exchange kernels: concatenated logits == unsharded forward.  Three forwards in a row (epochs, both buffer parities).
+    Runs in its own process: kernels of one rank WAIT for kernels of another, so anything in the process that synchronises the
+    device between them (a cuBLAS handle created late, a lazily loaded module) ends in the kernels' 10 s watchdog trap, and a
+    trapped context would take every later test of this process with it."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--virtual-model", tag, str(world)], capture_output=True,
+                       text=True, timeout=600, env=dict(os.environ, CUDA_MODULE_LOADING="EAGER", CUDA_DEVICE_MAX_CONNECTIONS="32"))
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+
+
+def _virtual_model_case(tag, world):
+    from caduceus_b200 import seqshard
     model, cfg = _model(tag, DEV)
     E, N = 2 * cfg.d_model, 16
     B, Ls = 2, 384
@@ -102,10 +113,16 @@ def test_sequence_sharded_forward_virtual_ranks(tag, world):
             full = model(ids).logits
         torch.cuda.synchronize()
         outs, errs = [None] * world, []
+        ready = threading.Barrier(world)
 
         def run(r):
             try:
                 with torch.cuda.stream(torch.cuda.Stream()), torch.no_grad(), seqshard.sequence_parallel(peer=peers[r]):
+                    # a NEW thread may have to create its cuBLAS handle (cublasCreate synchronises the device): do that, and anything
+                    # else a first GEMM on this thread / stream sets up, BEFORE any rank launches a kernel that waits for another rank
+                    a = torch.ones(64, 64, device=DEV, dtype=torch.bfloat16)
+                    (a @ a).sum().item()
+                    ready.wait(60)
                     outs[r] = model(ids[:, r * Ls:(r + 1) * Ls].contiguous()).logits
                     torch.cuda.current_stream().synchronize()
             except Exception as ex:      # noqa: BLE001
@@ -195,3 +212,11 @@ def test_sequence_sharded_forward_real_peers(tag):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run_procs(2, tag, "nccl", True)
+
+
+if __name__ == "__main__":          # subprocess entry of test_sequence_sharded_forward_virtual_ranks
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    if len(sys.argv) == 4 and sys.argv[1] == "--virtual-model":
+        _virtual_model_case(sys.argv[2], int(sys.argv[3]))
+        print("ok")

@@ -199,7 +199,7 @@ def test_scan_kernel_choice_per_call():
     assert CF.choose_scan_variant(bf, 16, 4, 512, 65536) == 20         # PS shard of a 2-way split
     assert CF.choose_scan_variant(bf, 16, 4, 512, 16384) == 3          # PS shard of an 8-way split: too few warps without time parallelism
     assert CF.choose_scan_variant(bf, 16, 4, 512, 1024) == 3
-    assert CF.choose_scan_variant(bf, 16, 64, 512, 8192) == 20         # a large batch of medium sequences
+    assert CF.choose_scan_variant(bf, 16, 64, 512, 8192) == 20         # a large batch of medium sequences (1024 warps, no time split)
     assert CF.choose_scan_variant(f32, 16, 4, 512, 131072) == 3
     old = CF.SCAN_VARIANT
     try:
@@ -212,13 +212,13 @@ def test_scan_kernel_choice_per_call():
 
 
 def test_segment_count_of_the_lane_per_channel_scan():
-    """variant 20: about two CTAs per SM (148 SMs when no device is visible), whole 256-token chunks, no segment shorter
+    """variant 20: about eight warps per SM (148 SMs when no device is visible), whole 256-token chunks, no segment shorter
     than 2048 tokens; CAD_SCAN_NSEG overrides."""
     from caduceus_b200 import functional as CF
-    assert CF.default_nseg(4, 512, 131072, 8) == 37          # Caduceus-PS headline: 4 jobs x 2 channel groups x 37 = 296 CTAs
-    assert CF.default_nseg(2, 512, 131072, 4) == 37          # Caduceus-Ph: 2 jobs x 4 groups x 37
+    assert CF.default_nseg(4, 512, 131072, 8) == 18          # Caduceus-PS headline: 4 jobs x 16 channel groups x 18 = 1152 warps
+    assert CF.default_nseg(2, 512, 131072, 4) == 37          # Caduceus-Ph: 2 jobs x 16 groups x 37 = 1184 warps
     assert CF.default_nseg(4, 512, 4096, 8) == 2 and CF.default_nseg(4, 512, 1024, 8) == 1
-    assert CF.default_nseg(64, 512, 131072, 8) == 2          # a large batch needs almost no time split
+    assert CF.default_nseg(64, 512, 131072, 8) == 1          # a large batch needs no time split
     old = CF.SCAN_NSEG
     try:
         CF.SCAN_NSEG = 9

@@ -15,7 +15,7 @@ from mamba_ssm.ops.triton.layernorm import RMSNorm, layer_norm_fn, rms_norm_fn
 import caduceus_oracle as CO
 
 MODEL_FIXTURES = ["ph_config0", "ps_config0", "ph_small", "ps_small", "ps_nonfused", "ph_nonfused_ln",
-                  "ps_ln_fp32res", "ph_mul_untied", "ph_unidir"]
+                  "ps_ln_fp32res", "ph_mul_untied", "ph_unidir", "ps_d118", "ph_d118"]
 
 
 # ---- closed-form known answers for the selective scan ----------------------------
@@ -101,7 +101,12 @@ def test_norm_restatement():
     assert torch.allclose(res, x + r) and torch.allclose(y, F.layer_norm(x + r, (16,), w, b, 1e-5), atol=1e-5)
     y2 = rms_norm_fn(x, w, None, eps=1e-5)
     assert torch.allclose(y2, x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w, atol=1e-6)
+    # upstream: a residual that is passed in keeps its dtype; residual_in_fp32 decides the dtype of a NEW residual stream only
     yb, resb = rms_norm_fn(x.bfloat16(), w.bfloat16(), None, residual=r.bfloat16(), prenorm=True, residual_in_fp32=True)
+    assert yb.dtype == torch.bfloat16 and resb.dtype == torch.bfloat16
+    yb, resb = rms_norm_fn(x.bfloat16(), w.bfloat16(), None, residual=r, prenorm=True, residual_in_fp32=False)
+    assert yb.dtype == torch.bfloat16 and resb.dtype == torch.float32
+    yb, resb = rms_norm_fn(x.bfloat16(), w.bfloat16(), None, residual=None, prenorm=True, residual_in_fp32=True)
     assert yb.dtype == torch.bfloat16 and resb.dtype == torch.float32
 
 
