@@ -114,6 +114,19 @@ class ConvFwdArgs(C.Structure):
                 ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32)]
 
 
+class HeadCeArgs(C.Structure):
+    _fields_ = [("hidden", _p), ("weight", _p), ("cmap", _p), ("labels", _p), ("loss_weights", _p),
+                ("loss_partial", _p), ("wsum_partial", _p), ("lse", _p), ("dloss_scale", _p), ("dhidden", _p), ("dwcat_partial", _p),
+                ("rows", _i64), ("D", _i64), ("V", _i64), ("width", _i64), ("ldh", _i64), ("lddh", _i64), ("ignore_index", _i64),
+                ("rcps", _i32), ("io_dtype", _i32), ("nblocks", _i32)]
+
+
+class WindowMeanArgs(C.Structure):
+    _fields_ = [("hidden", _p), ("variant_idx", _p), ("out", _p),
+                ("B", _i64), ("L", _i64), ("C", _i64), ("ldh", _i64), ("c0", _i64), ("ldo", _i64),
+                ("lo_half", _i32), ("half", _i32), ("flip_len", _i32), ("flip_ch", _i32), ("io_dtype", _i32)]
+
+
 class PeerCtx(C.Structure):
     _fields_ = [("peer_ws", _p), ("rank", _i32), ("world", _i32),
                 ("nseq_max", _i64), ("njobs_max", _i64), ("E", _i64), ("N", _i64)]
@@ -142,6 +155,10 @@ SYMBOLS = {
     "cad_peer_ws_bytes": (_i64, [_i32, _i64, _i64, _i64, _i64]),
     "cad_peer_halo_exchange": (C.c_int, [C.POINTER(PeerCtx), _p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _p]),
     "cad_peer_carry_exchange": (C.c_int, [C.POINTER(PeerCtx), _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
+    "cad_head_ce_blocks": (C.c_int, [_i64]),
+    "cad_head_ce_fwd": (C.c_int, [C.POINTER(HeadCeArgs), _p]),
+    "cad_head_ce_bwd": (C.c_int, [C.POINTER(HeadCeArgs), _p]),
+    "cad_window_mean": (C.c_int, [C.POINTER(WindowMeanArgs), _p]),
     "cad_hg38_batch_fwd": (C.c_int, [C.POINTER(Hg38BatchArgs), _p]),
     "cad_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double), _p]),
 }

@@ -466,6 +466,59 @@ def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, chann
 
 
 # =====================================================================================================
+# fused (RC-equivariant) LM head + masked cross-entropy (csrc/head_ce.cu)
+# =====================================================================================================
+class _HeadCeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight, labels, cmap, loss_weights, ignore_index):
+        _require_cuda(hidden, weight, labels)
+        lib = _lib.load()
+        width = hidden.shape[-1]
+        V, D = weight.shape
+        rcps = cmap is not None
+        h2, rows, ldh = _rows(hidden, width)
+        w = weight.to(h2.dtype).contiguous()
+        y = labels.reshape(-1).contiguous().long()
+        lw = None if loss_weights is None else loss_weights.reshape(-1).contiguous().float()
+        nb = lib.cad_head_ce_blocks(rows)
+        part = torch.empty(2, nb, device=h2.device, dtype=torch.float32)
+        lse = torch.empty(rows, device=h2.device, dtype=torch.float32)
+        a = _lib.HeadCeArgs(_ptr(h2), _ptr(w), _ptr(cmap), _ptr(y), _ptr(lw), _ptr(part[0]), _ptr(part[1]), _ptr(lse), None, None,
+                            None, rows, D, V, width, ldh, 0, int(ignore_index), int(rcps), _dt(h2), nb)
+        _lib.check(lib.cad_head_ce_fwd(C.byref(a), _stream()), "cad_head_ce_fwd")
+        _launched()
+        sums = part.sum(dim=1)                              # (loss sum, weight sum): deterministic two-stage reduction
+        ctx.save_for_backward(h2, w, y, cmap, lw, lse, sums)
+        ctx.meta = (rows, D, V, width, ldh, int(ignore_index), rcps, nb, hidden.shape, weight.dtype)
+        return sums[0] / sums[1]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        h2, w, y, cmap, lw, lse, sums = ctx.saved_tensors
+        rows, D, V, width, ldh, ignore_index, rcps, nb, hshape, wdtype = ctx.meta
+        lib = _lib.load()
+        scale = (dloss.float() / sums[1]).reshape(1).contiguous()
+        dh = torch.empty(rows, width, device=h2.device, dtype=h2.dtype)
+        dwp = torch.empty(nb, V, width, device=h2.device, dtype=torch.float32)
+        a = _lib.HeadCeArgs(_ptr(h2), _ptr(w), _ptr(cmap), _ptr(y), _ptr(lw), None, None, _ptr(lse), _ptr(scale), _ptr(dh), _ptr(dwp),
+                            rows, D, V, width, ldh, width, ignore_index, int(rcps), _dt(h2), nb)
+        _lib.check(lib.cad_head_ce_bwd(C.byref(a), _stream()), "cad_head_ce_bwd")
+        _launched()
+        dwcat = dwp.sum(dim=0)                              # (V, width)
+        dw = dwcat[:, :D]
+        if rcps:        # Wcat[v, D + c] = W[cmap[v], D - 1 - c]  ->  dW[cmap[v], D - 1 - c] += dWcat[v, D + c]
+            dw = dw.index_add(0, cmap, dwcat[:, D:].flip(-1))
+        return dh.view(hshape), dw.to(wdtype), None, None, None, None
+
+
+def lm_head_cross_entropy(hidden, weight, labels, cmap=None, loss_weights=None, ignore_index=-100):
+    """Masked-LM loss straight from the final hidden states: mean (or weight-normalised) cross-entropy of
+    `hidden @ Wcat^T` against `labels` over the rows with label != ignore_index, without materialising the logits.
+    hidden (..., D) for Caduceus-Ph, (..., 2 D) with cmap (V,) for the RC-equivariant head; weight (V, D)."""
+    return _HeadCeFn.apply(hidden, weight, labels, cmap, loss_weights, ignore_index)
+
+
+# =====================================================================================================
 # sequence sharding over NVLink peer memory (csrc/peer_exchange.cu): no library collective on the data path
 # =====================================================================================================
 def peer_ws_bytes(world, nseq_max, njobs_max, E, N):

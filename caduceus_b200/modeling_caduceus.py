@@ -331,6 +331,11 @@ class CaduceusForMaskedLM(CaduceusPreTrainedModel):
         outputs = self.caduceus(input_ids=input_ids, inputs_embeds=inputs_embeds,
                                 output_hidden_states=output_hidden_states, return_dict=return_dict)
         hidden_states = outputs[0] if isinstance(outputs, (tuple, BaseModelOutputWithNoAttention)) else outputs
+        if labels is not None and getattr(self.config, "fused_head_loss", False) and hidden_states.is_cuda:
+            # opt-in (config.fused_head_loss = True; not a reference field): the masked-LM loss straight from the hidden states —
+            # head GEMM and cross-entropy only at the non-ignored positions, fp32 (B, L, V) logits never materialised
+            # (csrc/head_ce.cu).  `logits` of the output is None in this mode.
+            return self._fused_loss_output(hidden_states, labels, loss_weights, outputs, return_dict)
         logits = self.lm_head(hidden_states).float()
 
         loss = None
@@ -347,6 +352,30 @@ class CaduceusForMaskedLM(CaduceusPreTrainedModel):
             output = (logits,) + rest
             return (loss,) + output if loss is not None else output
         return MaskedLMOutput(loss=loss, logits=logits, hidden_states=outputs.hidden_states)
+
+
+def _fused_loss_output(self, hidden_states, labels, loss_weights, outputs, return_dict):
+    ignore = getattr(self.config, "pad_token_id", None)
+    ignore = -100 if ignore is None else ignore
+    head = self.lm_head
+    if self.config.rcps:
+        if head.lm_head.bias is not None:
+            raise NotImplementedError("fused_head_loss: a head bias is not supported")
+        weight, cmap = head.weight, head.complement_map
+    else:
+        if head.bias is not None:
+            raise NotImplementedError("fused_head_loss: a head bias is not supported")
+        weight, cmap = head.weight, None
+    if loss_weights is not None:          # like the reference (ref:caduceus/modeling_caduceus.py:291), in place
+        loss_weights.view(-1)[labels.view(-1) == ignore] = 0.0
+    loss = CF.lm_head_cross_entropy(hidden_states, weight, labels, cmap=cmap, loss_weights=loss_weights, ignore_index=ignore)
+    if not return_dict:
+        rest = tuple(outputs[1:]) if isinstance(outputs, tuple) else ()
+        return (loss, None) + rest
+    return MaskedLMOutput(loss=loss, logits=None, hidden_states=outputs.hidden_states)
+
+
+CaduceusForMaskedLM._fused_loss_output = _fused_loss_output
 
 
 class CaduceusForSequenceClassification(CaduceusPreTrainedModel):

@@ -308,6 +308,33 @@ typedef struct {
 } cad_conv_fwd_args;
 int cad_conv_silu_fwd(const cad_conv_fwd_args* a, void* stream);
 
+/* ---- "next" row N3: fused (RC-equivariant) LM head + masked cross-entropy.  Replaces
+ *      logits = lm_head(hidden).float() over all positions (ref:caduceus/modeling_caduceus.py:474-476; RCPS head
+ *      ref:caduceus/modeling_rcps.py:233-246) followed by cross_entropy / weighted_cross_entropy with ignore_index
+ *      (ref:caduceus/modeling_caduceus.py:279-294,478-482): the fp32 (B, L, V) logits are never materialised, ignored rows cost one
+ *      label load.  Wcat[v, c] = W[v, c] (c < D);  Wcat[v, D + c] = W[cmap[v], D - 1 - c] (RCPS), read in place.
+ *        forward : loss_partial / wsum_partial (nblocks) — the caller sums them: loss = sum(loss_partial) / sum(wsum_partial);
+ *                  lse (rows) saved for the backward (0 for ignored rows)
+ *        backward: dloss_scale (1 device float) = dloss / sum(wsum);  dhidden (rows, width) io dtype, zero rows for ignored tokens;
+ *                  dwcat_partial (nblocks, V, width) fp32 — the caller sums over blocks and folds the RC half back into (V, D).     */
+typedef struct {
+  const void* hidden;          /* (rows, width) pitch ldh, io dtype; width = D (Ph) or 2 D (RCPS) */
+  const void* weight;          /* (V, D) table, io dtype */
+  const int64_t* cmap;         /* (V) complement map, RCPS only */
+  const int64_t* labels;       /* (rows) */
+  const float* loss_weights;   /* (rows) or NULL */
+  float* loss_partial; float* wsum_partial;   /* (nblocks) forward outputs */
+  float* lse;                  /* (rows): forward output, backward input */
+  const float* dloss_scale;    /* backward: 1 float on the device */
+  void* dhidden;               /* backward: (rows, width) pitch lddh */
+  float* dwcat_partial;        /* backward: (nblocks, V, width) */
+  int64_t rows, D, V, width, ldh, lddh, ignore_index;
+  int32_t rcps, io_dtype, nblocks;
+} cad_head_ce_args;
+int cad_head_ce_blocks(int64_t rows);            /* nblocks both passes want for `rows` */
+int cad_head_ce_fwd(const cad_head_ce_args* a, void* stream);
+int cad_head_ce_bwd(const cad_head_ce_args* a, void* stream);
+
 /* ---- "next" row N2: GPU-side hg38 batch preparation, integer / byte work, bit-exact.
  *      raw (B, L) ASCII bytes of the FASTA slices -> data, target (B, L) int64:
  *        optional per-row string reverse complement (ref:src/dataloaders/utils/rc.py:17-26),
@@ -322,6 +349,20 @@ typedef struct {
   int64_t n_id, pad_id, mask_id;
 } cad_hg38_batch_args;
 int cad_hg38_batch_fwd(const cad_hg38_batch_args* a, void* stream);
+
+/* ---- "next" row N4: windowed mean of last-layer hidden states around a variant — the pooling of the reference's
+ *      VEP dump loop (arange + clamp + gather + mean, ref:vep_embeddings.py:278-311) on a VIEW of the stored tensor:
+ *        V[b, r, c] = hidden[b, flip_len ? L-1-r : r, c0 + (flip_ch ? C-1-c : c)]
+ *        out[b, c]  = mean over j in [idx_b - lo_half, idx_b + half] of V[b, clamp(j, 0, L-1), c]
+ *      so that the RC view (ref:vep_embeddings.py:355-366: `.contiguous().flip(dims=[1, 2])` of half the channels) is read in place. */
+typedef struct {
+  const void* hidden;            /* (B, L, ldh) token rows, io dtype */
+  const int64_t* variant_idx;    /* (B) on the device */
+  void* out;                     /* (B, ldo), io dtype; columns [0, C) written */
+  int64_t B, L, C, ldh, c0, ldo;
+  int32_t lo_half, half, flip_len, flip_ch, io_dtype;
+} cad_window_mean_args;
+int cad_window_mean(const cad_window_mean_args* a, void* stream);
 
 /* ---- micro-benchmarks of the pipes that bound the scan (MUFU ex2, FFMA), used by bench.py to quote
  *      "fraction of measured MUFU peak" beside the HBM fraction.  Writes ops/s.          */

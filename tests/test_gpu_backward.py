@@ -148,3 +148,72 @@ def test_embedding_backward_any_width_and_vocabulary(D, V, rcps):
     assert torch.equal(out, ref)                      # index work: bit-exact
     (dWr,) = torch.autograd.grad(ref, Wr, gout)
     assert torch.allclose(dW, dWr, rtol=1e-5, atol=1e-4), (dW - dWr).abs().max()
+
+
+@pytest.mark.parametrize("rcps", [False, True])
+@pytest.mark.parametrize("dtype,weighted", [(torch.float32, False), (torch.bfloat16, False), (torch.float32, True)])
+def test_fused_lm_head_cross_entropy_vs_reference_formula(rcps, dtype, weighted):
+    """csrc/head_ce.cu against the literal reference: logits = head(hidden).float() (RCPS: x1 W^T +
+    flip(x2) W[cmap]^T, ref:caduceus/modeling_rcps.py:233-246), then (weighted) cross-entropy with ignore_index
+    (ref:caduceus/modeling_caduceus.py:279-294) — loss, d hidden (zero rows at ignored positions) and d weight."""
+    from caduceus_b200 import functional as CF
+    g = torch.Generator().manual_seed(3 + rcps)
+    B, L, D, V = 2, 700, 96, 16
+    width = 2 * D if rcps else D
+    hid = torch.randn(B, L, width, generator=g).to(DEV).to(dtype).requires_grad_(True)
+    W = (0.3 * torch.randn(V, D, generator=g)).to(DEV).requires_grad_(True)
+    cmap = torch.tensor([0, 1, 2, 3, 4, 5, 6, 10, 9, 8, 7, 11, 12, 13, 14, 15], device=DEV) if rcps else None
+    labels = torch.randint(0, 12, (B, L), generator=g).to(DEV)
+    labels[torch.rand(B, L, generator=g).to(DEV) > 0.15] = 4                 # ~85 % ignored, as in MLM
+    lw = torch.rand(B, L, generator=g).to(DEV) if weighted else None
+    loss = CF.lm_head_cross_entropy(hid, W, labels, cmap=cmap, loss_weights=None if lw is None else lw.clone(), ignore_index=4)
+    dh, dw = torch.autograd.grad(loss, (hid, W))
+
+    hid_r = hid.detach().clone().requires_grad_(True)
+    W_r = W.detach().clone().requires_grad_(True)
+    Wc = W_r.to(dtype)
+    logits = torch.nn.functional.linear(hid_r[..., :D], Wc)
+    if rcps:
+        logits = logits + torch.nn.functional.linear(torch.flip(hid_r[..., D:], dims=[-1]), Wc[cmap, :])
+    logits = logits.float().view(-1, V)
+    y = labels.view(-1)
+    if weighted:
+        ce = torch.nn.functional.cross_entropy(logits, y, ignore_index=4, reduction="none")
+        w = lw.view(-1).clone()
+        w[y == 4] = 0.0
+        ref = (ce * (w / w.sum())).sum()
+    else:
+        ref = torch.nn.functional.cross_entropy(logits, y, ignore_index=4)
+    dh_r, dw_r = torch.autograd.grad(ref, (hid_r, W_r))
+    rt, at = (1e-4, 1e-6) if dtype == torch.float32 else (2e-2, 2e-4)
+    assert abs(loss.item() - ref.item()) <= rt * abs(ref.item()) + 1e-5, (loss.item(), ref.item())
+    assert (dh.float()[labels == 4] == 0).all()
+    _grad_close(dh.float(), dh_r.float(), rt * 10, at * 10, "d hidden")
+    _grad_close(dw, dw_r, rt * 10, at * 10, "d weight")
+
+
+@pytest.mark.parametrize("tag", ["ps_small", "ph_small"])
+def test_model_fused_head_loss_matches_the_logits_path(tag):
+    """config.fused_head_loss: same loss and parameter gradients as the reference-shaped path that materialises the logits."""
+    import caduceus
+    fx = golden(f"model_{tag}.pt")
+    grads = {}
+    for fused in (False, True):
+        cfg = caduceus.CaduceusConfig(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in fx["config"].items()})
+        cfg.pad_token_id = 4
+        cfg.fused_head_loss = fused
+        model = caduceus.CaduceusForMaskedLM(cfg)
+        model.load_state_dict(fx["state_dict"])
+        model = model.to(DEV).train()
+        ids = fx["input_ids"]
+        g = torch.Generator().manual_seed(0)
+        labels = ids.clone()
+        labels[torch.rand(ids.shape, generator=g) > 0.3] = 4
+        out = model(ids.to(DEV), labels=labels.to(DEV))
+        assert (out.logits is None) == fused
+        out.loss.backward()
+        grads[fused] = (out.loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert abs(grads[True][0] - grads[False][0]) < 1e-5 * max(1.0, abs(grads[False][0]))
+    assert set(grads[True][1]) == set(grads[False][1])
+    for n, gr in grads[False][1].items():
+        _grad_close(grads[True][1][n], gr, 1e-3, 1e-5, f"d {n}")

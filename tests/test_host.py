@@ -36,7 +36,8 @@ def test_struct_sizes_match_header_layout():
                        ("cad_add_norm_bwd_args", _lib.AddNormBwdArgs), ("cad_embedding_bwd_args", _lib.EmbeddingBwdArgs),
                        ("cad_scan_bwd_args", _lib.ScanBwdArgs), ("cad_conv_bwd_args", _lib.ConvBwdArgs),
                        ("cad_conv_xproj_args", _lib.ConvXprojArgs), ("cad_scan_fixup_args", _lib.ScanFixupArgs),
-                       ("cad_hg38_batch_args", _lib.Hg38BatchArgs),
+                       ("cad_hg38_batch_args", _lib.Hg38BatchArgs), ("cad_head_ce_args", _lib.HeadCeArgs), ("cad_window_mean_args", _lib.WindowMeanArgs),
+                       ("cad_peer_ctx", _lib.PeerCtx),
                        ("cad_scan_adjoint_args", _lib.ScanAdjointArgs)):
         names = []
         for decl in structs[cname].split(";"):

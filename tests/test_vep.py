@@ -99,3 +99,47 @@ def test_variant_embeddings_on_the_cuda_backbone():
                       ("rc_concat_avg_ws", R.extract_embeddings(r_ref, r_alt, vi))):
         assert out[key].shape == (B, 2 * cfg.d_model)
         assert torch.allclose(out[key].float(), want.float(), rtol=3e-3, atol=5e-3), (key, (out[key] - want).abs().max())
+
+
+def test_dump_split_writes_the_reference_storage_dict(tmp_path):
+    """dump_split == the reference loop's storage_dict after concat_storage_dict_values (ref:vep_embeddings.py:329-399): same keys,
+    batches concatenated in order, embeddings equal to the per-batch extraction."""
+    torch.manual_seed(2)
+    B, L, C, nb = 2, 1700, 8, 3
+    m = _FakeBackbone(C)
+    batches = []
+    for i in range(nb):
+        ref = torch.randint(7, 11, (B, L))
+        alt = ref.clone()
+        alt[:, 100 + i] = (alt[:, 100 + i] - 7 + 1) % 4 + 7
+        batches.append({"ref_input_ids": ref, "alt_input_ids": alt, "variant_idx": torch.full((B,), 100 + i),
+                        "chromosome": torch.full((B,), i), "labels": torch.tensor([0, 1]), "distance_to_nearest_tss": torch.rand(B),
+                        "tissue_embed": torch.full((B,), 7 - i)})
+    path = tmp_path / "test_embeds_0.pt"
+    got = V.dump_split(m, batches, path=str(path), rcps=True)
+    assert tuple(got) == V.STORAGE_KEYS and all(v.shape[0] == nb * B for v in got.values())
+    loaded = torch.load(str(path))
+    for i, b in enumerate(batches):
+        one = V.variant_embeddings(m, b["ref_input_ids"], b["alt_input_ids"], variant_idx=b["variant_idx"], rcps=True)
+        for key in ("concat_avg_ws", "rc_concat_avg_ws"):
+            assert torch.equal(loaded[key][i * B:(i + 1) * B], one[key])
+        assert torch.equal(loaded["chromosome"][i * B:(i + 1) * B], b["chromosome"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_window_mean_kernel_matches_reference_gather(dtype):
+    """csrc/vep_pool.cu on a channel slice of a wider tensor, windows clamped at both ends, all four (flip_len, flip_ch) views."""
+    g = torch.Generator().manual_seed(5)
+    B, L, W = 5, 5000, 48
+    hid = torch.randn(B, L, W, generator=g).to("cuda").to(dtype)
+    vi = torch.tensor([2500, 3, 4996, 0, 4999], device="cuda")
+    for sl in (slice(0, 24), slice(24, 48)):
+        for fl in (False, True):
+            for fc in (False, True):
+                view = hid[..., sl]
+                want_src = view.flip(dims=[1]) if fl else view
+                want_src = want_src.flip(dims=[2]) if fc else want_src
+                want = R.extract_embeddings(want_src.float(), want_src.float(), vi)[:, :24]
+                got = V._window_mean(view, vi, 768, 768, flip_len=fl, flip_ch=fc)
+                assert torch.allclose(got.float(), want, rtol=2e-3 if dtype == torch.float16 else 1e-5, atol=2e-3 if dtype == torch.float16 else 1e-5)
