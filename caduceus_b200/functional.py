@@ -383,9 +383,7 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     """Scan variant 20 (lane = channel, csrc/scan_fwd_v20.cuh): token-major copy of B / C, every segment scanned from a zero
     state, carries composed (cad_seg_carry) and added in place by the segment mode of the fix-up kernel.  `a` is the
     marshalled argument block of scan_fwd (reused so that the two paths cannot drift apart).  cutoff_log2: a carry term is
-    dropped once its decay factor is below 2^cutoff; default 2^-16 for bf16 and 2^-20 for fp16 outputs — with all 16 states of a
-    channel at the threshold and |C h0| as large as the output itself that is 1/16 (1/32) of an output ulp (the multi-GPU path
-    keeps 2^-40 because it also serves fp32 I/O).
+    dropped once its decay factor is below 2^cutoff (None = default_cutoff_log2(dtype)).
     Returns (out, hlast, dtsum, seg_ctx).  want_state (a sequence SHARD): the local carries are NOT applied
     here; hlast / dtsum are the shard's zero-carry end state and sum dt for the all_gather, and seg_ctx goes to
     scan_fixup(..., h0, seg_ctx=seg_ctx), which applies the shard's carry-in and the local carries in ONE pass."""
@@ -395,7 +393,7 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     njobs, twoN, ldbc = bc.shape
     E, N, dev = a.E, twoN // 2, xz.device
     if cutoff_log2 is None:
-        cutoff_log2 = -16.0 if xz.dtype == torch.bfloat16 else -20.0
+        cutoff_log2 = default_cutoff_log2(xz.dtype)
     W = warps_per_cta if warps_per_cta > 0 else v20_warps_per_cta(njobs, E)
     nseg = default_nseg(njobs, E, L, W) if nseg is None else int(nseg)
     Lp = round_up(max(L, 1), 256)
@@ -436,9 +434,15 @@ def scan_fwd_segmented(xz, delta, bc, packed, jobs, L, out, a, nseg=None, warps_
     return out, hlast, dtsum, seg_ctx
 
 
-def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, channels_per_cta=0, seg_ctx=None):
+def default_cutoff_log2(dtype):
+    """Carry terms are dropped once their decay factor is below 2^cutoff: 2^-16 for bf16 and 2^-20 for fp16 outputs — with all 16
+    states of a channel at the threshold and |C h0| as large as the output itself that is 1/16 (1/32) of an output ulp — 2^-40 for fp32."""
+    return -16.0 if dtype == torch.bfloat16 else -20.0 if dtype == torch.float16 else -40.0
+
+
+def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=None, channels_per_cta=0, seg_ctx=None):
     """In place: out += silu(z) * sum_n C * exp2(A2 * cumsum(dt)) * h0 — turns a zero-carry shard scan into the scan
-    with carry-in h0 (njobs, E, N).  See csrc/scan_fixup.cu."""
+    with carry-in h0 (njobs, E, N).  See csrc/scan_fixup.cu.  cutoff_log2: None = default_cutoff_log2(dtype)."""
     lib = _lib.load()
     seq, pset, rev = jobs
     _, _, dt_b, A2, _ = packed
@@ -446,6 +450,8 @@ def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=-40.0, chann
     E = twoE // 2
     njobs, twoN, ldbc = bc.shape
     h0 = h0.contiguous()
+    if cutoff_log2 is None:
+        cutoff_log2 = default_cutoff_log2(xz.dtype)
     a = _lib.ScanFixupArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
                            _ptr(rev), _ptr(h0), L, E, twoN // 2, ldxz, delta.stride(1), ldbc, out.stride(1),
                            nseq, njobs, _dt(xz), channels_per_cta, float(cutoff_log2))

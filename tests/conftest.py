@@ -3,14 +3,9 @@ import sys
 
 import pytest
 
-# the virtual-rank tests of tests/test_gpu_multi.py run kernels that WAIT for kernels of other streams: every stream needs its own
-# hardware queue (default: 8 connections shared by all streams).  Must be set before the CUDA context exists.
+# tests/test_gpu_multi.py runs kernels that WAIT for kernels of other streams (virtual ranks, in subprocesses of their own): every
+# stream needs its own hardware queue (default: 8 connections shared by all streams).  Must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# ... and every kernel must be resident before a waiting kernel runs: with lazy module loading (the CUDA 12 default) the FIRST launch
-# of a kernel may synchronise the context, which deadlocks against a kernel of another virtual rank that spins until that launch
-# has happened (CUDA programming guide, "Lazy Loading": concurrent execution is not guaranteed across a first launch).  Separate
-# processes — the production layout, one rank per process — have separate contexts and are not affected.
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE = os.path.join(ROOT, "oracle")
