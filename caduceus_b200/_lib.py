@@ -53,7 +53,7 @@ class ScanFwdArgs(C.Structure):
                 ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64), ("ldo", _i64),
                 ("nseq", _i32), ("njobs", _i32), ("npset", _i32), ("io_dtype", _i32), ("channels_per_cta", _i32),
                 ("state_only", _i32), ("variant", _i32),
-                ("bcT", _p), ("nseg", _i32), ("seg_state", _p), ("seg_dtsum", _p)]
+                ("bcT", _p), ("nseg", _i32), ("seg_state", _p), ("seg_dtsum", _p), ("chunk_dtsum", _p)]
 
 
 class ScanFixupArgs(C.Structure):
@@ -152,6 +152,7 @@ SYMBOLS = {
     "cad_bimamba_scan_adjoint": (C.c_int, [C.POINTER(ScanAdjointArgs), _p]),
     "cad_bc_transpose": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "cad_seg_carry": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
+    "cad_shard_seg_carry": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f32, _p]),
     "cad_peer_ws_bytes": (_i64, [_i32, _i64, _i64, _i64, _i64]),
     "cad_peer_halo_exchange": (C.c_int, [C.POINTER(PeerCtx), _p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _p]),
     "cad_peer_carry_exchange": (C.c_int, [C.POINTER(PeerCtx), _p, _p, _p, _p, _p, _i32, _p, _p, _p]),

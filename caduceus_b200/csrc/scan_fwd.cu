@@ -290,6 +290,7 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     const int64_t tseg_next = (REV ? pcidx - 1 : pcidx + 1) * CH + (int64_t)seg * TOK;
     const T* pre_cur = pre_ptr((int)(c & 1));
     T* pre_next = pre_ptr((int)((c + 1) & 1));
+    const float dt_before = dt_total;
     if (tail)
       scan_chunk<T, N, TOK, REV, true, STATE_ONLY>(a, sm, lane, seg, poff, xrow, zrow, drow, orow, tseg, active, cw, cb, dtb, Dk, hal,
                                   prev3, dt_total, my_carry, my_a2, parity, issue_next, tmap, next_c1, job_row, pre_cur, pre_next,
@@ -302,6 +303,12 @@ __device__ __forceinline__ void scan_job(const cad_scan_fwd_args& a, const CUten
     if (a.chunk_state) {
       __syncwarp();
       if (active && lane < N) a.chunk_state[(((int64_t)job * E + ch) * nchunks + c) * N + lane] = my_carry[lane];
+    }
+    if (a.chunk_dtsum) {                         // sum of dt over this logical chunk (segment-parallel carry fix-up of a shard)
+      float cs = dt_total - dt_before;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+      if (active && lane == 0) a.chunk_dtsum[((int64_t)job * E + ch) * nchunks + c] = cs;
     }
   }
 

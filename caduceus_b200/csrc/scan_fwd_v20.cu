@@ -88,7 +88,47 @@ __global__ void __launch_bounds__(256) seg_carry_kernel(const float* __restrict_
   if (dtsum && n == 0) dtsum[j * E + e] = dsum;
 }
 
+// carry[j, s, e, n] = h0[j, e, n] * exp2(A2 * sum of dt over the logical segments before s), exactly 0 once the exponent is below the
+// cut-off.  One thread per (job, channel, state); a segment = per512 physical 512-token chunks, whose sums of dt the time-parallel
+// scan wrote in LOGICAL chunk order (physical chunk pc of a reversed job = logical chunk nchunks - 1 - pc).
+__global__ void __launch_bounds__(256) shard_seg_carry_kernel(const float* __restrict__ chunk_dtsum, const float* __restrict__ A2,
+                                                              const int32_t* __restrict__ pset_of_job, const int32_t* __restrict__ rev_of_job,
+                                                              const float* __restrict__ h0, float* __restrict__ carry, int64_t njobs,
+                                                              int64_t E, int64_t nchunks, int64_t nseg, int64_t per512, float cutoff_log2) {
+  constexpr int N = 16;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= njobs * E * N) return;
+  const int64_t n = i % N, e = (i / N) % E, j = i / (N * E);
+  const float a2 = A2[((int64_t)pset_of_job[j] * E + e) * N + n];
+  const bool rev = rev_of_job[j] != 0;
+  const float* cd = chunk_dtsum + (j * E + e) * nchunks;
+  const float h = h0[(j * E + e) * N + n];
+  float cum = 0.f;
+  for (int64_t sl = 0; sl < nseg; ++sl) {
+    const float x = a2 * cum;
+    carry[((j * nseg + sl) * E + e) * N + n] = (sl == 0) ? h : (x < cutoff_log2 ? 0.f : h * ex2(x));
+    const int64_t k = rev ? nseg - 1 - sl : sl;                 // physical block of this logical segment
+    const int64_t p0 = k * per512, p1 = min((k + 1) * per512, nchunks);
+    for (int64_t pc = p0; pc < p1; ++pc) cum += cd[rev ? nchunks - 1 - pc : pc];
+  }
+}
+
 }  // namespace cad
+
+extern "C" int cad_shard_seg_carry(const float* chunk_dtsum, const float* A2, const int32_t* pset_of_job, const int32_t* rev_of_job,
+                                   const float* h0, float* carry, int64_t njobs, int64_t E, int64_t nchunks, int64_t nseg,
+                                   int64_t per512, float cutoff_log2, void* stream_) {
+  using namespace cad;
+  CAD_REQUIRE(chunk_dtsum && A2 && pset_of_job && rev_of_job && h0 && carry, "cad_shard_seg_carry: null pointer");
+  CAD_REQUIRE(njobs > 0 && E > 0 && nchunks > 0 && nseg > 0 && per512 > 0 && (nseg - 1) * per512 < nchunks && nseg * per512 >= nchunks,
+              "cad_shard_seg_carry: nseg segments of per512 chunks must tile the nchunks chunks");
+  CAD_REQUIRE(cutoff_log2 < 0.f, "cad_shard_seg_carry: cutoff_log2 must be negative");
+  const int64_t n = njobs * E * 16;
+  shard_seg_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      chunk_dtsum, A2, pset_of_job, rev_of_job, h0, carry, njobs, E, nchunks, nseg, per512, cutoff_log2);
+  CAD_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int cad_bc_transpose(const float* bc, float* bcT, int64_t njobs, int64_t N2, int64_t L, int64_t ldbc, void* stream_) {
   using namespace cad;

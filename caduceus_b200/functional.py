@@ -323,10 +323,15 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     nchunks = (L + chunk - 1) // chunk
     cstate = (torch.empty(njobs, E, nchunks, N, device=xz.device, dtype=torch.float32)
               if want_chunk_state else None)
+    # a zero-carry shard scan (want_state, no carry-in) on the time-parallel kernel also reports the sum of dt per 512-token chunk,
+    # so that scan_fixup can apply the shard's carry-in to several segments in parallel (shard_fixup_plan)
+    plan = shard_fixup_plan(L) if (variant == 3 and want_state and h0 is None and not state_only and not want_chunk_state) else None
+    chunk_dt = torch.empty(njobs, E, nchunks, device=xz.device, dtype=torch.float32) if plan is not None else None
     a = _lib.ScanFwdArgs(
         _ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(conv_w4), _ptr(conv_b), _ptr(dt_b), _ptr(A2), _ptr(Dk),
         _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(h0), _ptr(hlast), _ptr(dtsum), _ptr(cstate),
         L, E, N, 4, ldxz, delta.stride(1), ldbc, ldxz, nseq, njobs, P, _dt(xz), channels_per_cta, int(state_only), variant)
+    a.chunk_dtsum = _ptr(chunk_dt)
     if variant == 20:
         if not plain:
             raise RuntimeError("scan variant 20 covers inference only (no carry-in at launch, saved chunk states or state-only "
@@ -344,7 +349,23 @@ def scan_fwd(xz, delta, bc, packed, jobs, L, *, halo=None, h0=None, want_state=F
     if ev is not None:
         ev[1].record()
         SCAN_EVENTS.append(ev)
+    if plan is not None:
+        return out, hlast, dtsum, {"chunk_dtsum": chunk_dt, "nseg": plan[0], "per512": plan[1], "nchunks": nchunks}
     return out, hlast, dtsum, cstate
+
+
+def shard_fixup_plan(L):
+    """(nseg, per512) for the segment-parallel carry fix-up of a shard of L tokens scanned by the time-parallel kernel, or None when
+    the serial whole-shard form is used: segments of `per512` physical 512-token chunks (>= 2048 tokens, at most 16 segments) that the
+    fix-up kernel's own block geometry (ceil(ceil(L / 256) / nseg) 256-token chunks per block) reproduces exactly."""
+    nch512, nch256 = (L + 511) // 512, (L + 255) // 256
+    if nch512 < 8:
+        return None
+    per512 = max(4, -(-nch512 // 16))
+    nseg = -(-nch512 // per512)
+    if nseg < 2 or -(-nch256 // nseg) != 2 * per512:
+        return None
+    return nseg, per512
 
 
 def v20_warps_per_cta(njobs, E):
@@ -455,7 +476,18 @@ def scan_fixup(xz, delta, bc, out, packed, jobs, L, h0, cutoff_log2=None, channe
     a = _lib.ScanFixupArgs(_ptr(xz), _ptr(delta), _ptr(bc), _ptr(out), _ptr(dt_b), _ptr(A2), _ptr(seq), _ptr(pset),
                            _ptr(rev), _ptr(h0), L, E, twoN // 2, ldxz, delta.stride(1), ldbc, out.stride(1),
                            nseq, njobs, _dt(xz), channels_per_cta, float(cutoff_log2))
-    if seg_ctx is not None:
+    if seg_ctx is not None and "chunk_dtsum" in seg_ctx:
+        # `out` came from the time-parallel kernel (one zero-carry scan of the whole shard): decay the shard's carry-in to the start
+        # of every segment (cad_shard_seg_carry) and fix all segments up in parallel — the serial form walks the slow channels through
+        # the whole shard with a few warps per SM, which is what bounded the 8-way split
+        nseg = seg_ctx["nseg"]
+        carry = torch.empty(njobs, nseg, E, twoN // 2, device=xz.device, dtype=torch.float32)
+        _lib.check(lib.cad_shard_seg_carry(_ptr(seg_ctx["chunk_dtsum"]), _ptr(A2), _ptr(pset), _ptr(rev), _ptr(h0), _ptr(carry),
+                                           njobs, E, seg_ctx["nchunks"], nseg, seg_ctx["per512"], float(cutoff_log2), _stream()),
+                   "cad_shard_seg_carry")
+        _launched()
+        a.nseg, a.seg_carry, a.seg_first = nseg, _ptr(carry), 1
+    elif seg_ctx is not None:
         # `out` came from scan variant 20 (every segment scanned from zero): compose the carry of every segment from the shard's
         # carry-in h0 and the segment end states, and fix up ALL segments (the first one included) in this one launch
         nseg = seg_ctx["nseg"]

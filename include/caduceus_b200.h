@@ -160,6 +160,10 @@ typedef struct {
                                from a ZERO state: with nseg > 1 `out` still lacks the carries (cad_seg_carry + cad_bimamba_scan_fixup) */
   float* seg_state;         /* (njobs, nseg, E, N) end state of every LOGICAL segment scanned from zero; required when nseg > 1 */
   float* seg_dtsum;         /* (njobs, nseg, E) sum of dt over the segment */
+  /* variant 3 only, optional (NULL): */
+  float* chunk_dtsum;       /* (njobs, E, nchunks) sum of dt over every 512-token LOGICAL chunk (nchunks = ceil(L / 512); physical
+                               chunk pc of a reversed job is logical chunk nchunks - 1 - pc): lets cad_shard_seg_carry split the
+                               carry fix-up of a sequence shard into segments that run in parallel */
 } cad_scan_fwd_args;
 int cad_bimamba_scan_fwd(const cad_scan_fwd_args* a, void* stream);
 int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512) */
@@ -170,8 +174,17 @@ int cad_scan_chunk_len(void);      /* logical tokens per saved chunk state (512)
  *                       carry[j, 0] = h0[j] (or 0),  carry[j, s+1] = exp2(A2 * seg_dtsum[j, s]) * carry[j, s] + seg_state[j, s]
  *                     and, optionally, what a sequence shard hands to its neighbours: hlast[j] = the state after the last
  *                     segment, dtsum[j] = sum over the segments of seg_dtsum.  h0 / carry / hlast / dtsum may be NULL.  (N == 16)
- *   the carries are then applied by cad_bimamba_scan_fixup with nseg / seg_carry set (seg_first = 1 when h0 was given).      */
+ *   the carries are then applied by cad_bimamba_scan_fixup with nseg / seg_carry set (seg_first = 1 when h0 was given).
+ *   cad_shard_seg_carry: the carry-in h0 of a sequence SHARD scanned by variant 3 from a zero state (which carries its own state
+ *                     from chunk to chunk), decayed to the start of every segment of `per512` physical 512-token chunks:
+ *                       carry[j, s] = exp2(A2 * sum of dt over the logical segments before s) * h0[j],  entries whose exponent has
+ *                       fallen below cutoff_log2 set to exactly 0 (the fix-up skips them) — so that cad_bimamba_scan_fixup with
+ *                       nseg / seg_carry / seg_first = 1 applies the shard's carry to all segments IN PARALLEL instead of walking
+ *                       each channel serially.  nseg = ceil(nchunks / per512); requires ceil(ceil(L/256) / nseg) == 2 * per512.    */
 int cad_bc_transpose(const float* bc, float* bcT, int64_t njobs, int64_t N2, int64_t L, int64_t ldbc, void* stream);
+int cad_shard_seg_carry(const float* chunk_dtsum, const float* A2, const int32_t* pset_of_job, const int32_t* rev_of_job,
+                        const float* h0, float* carry, int64_t njobs, int64_t E, int64_t nchunks, int64_t nseg, int64_t per512,
+                        float cutoff_log2, void* stream);
 int cad_seg_carry(const float* seg_state, const float* seg_dtsum, const float* A2, const int32_t* pset_of_job, const float* h0,
                   float* carry, float* hlast, float* dtsum, int64_t njobs, int64_t nseg, int64_t E, void* stream);
 

@@ -21,7 +21,7 @@ def pytest_configure(config):
 
 def golden(name):
     import torch
-    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=True)
 
 
 @pytest.fixture(scope="session")

@@ -185,7 +185,8 @@ def test_fused_lm_head_cross_entropy_vs_reference_formula(rcps, dtype, weighted)
     else:
         ref = torch.nn.functional.cross_entropy(logits, y, ignore_index=4)
     dh_r, dw_r = torch.autograd.grad(ref, (hid_r, W_r))
-    rt, at = (1e-4, 1e-6) if dtype == torch.float32 else (2e-2, 2e-4)
+    # bf16: the reference rounds its logits to bf16 before the softmax; here they stay fp32 — compare at bf16 resolution of the range
+    rt, at = (1e-4, 1e-6) if dtype == torch.float32 else (2e-2, 2e-3)
     assert abs(loss.item() - ref.item()) <= rt * abs(ref.item()) + 1e-5, (loss.item(), ref.item())
     assert (dh.float()[labels == 4] == 0).all()
     _grad_close(dh.float(), dh_r.float(), rt * 10, at * 10, "d hidden")
