@@ -308,6 +308,10 @@ typedef struct {
   int64_t ldT;              /* rows per job of bcT (ceil256(L)) */
 } cad_conv_xproj_args;
 int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
+/* The same operator with both projections on the 5th-generation tensor cores (tcgen05.mma issued by one thread per CTA,
+ * accumulators in tensor memory, read back with tcgen05.ld; csrc/xproj_umma.cu): persistent CTAs, two per SM.  Same
+ * argument block and outputs; d_inner may be any multiple of 64 up to 2048 and ldd need not be a multiple of 16.      */
+int cad_conv_xproj_umma_fwd(const cad_conv_xproj_args* a, void* stream);
 
 /* unfused helper (fp32 I/O and the training path, which needs u for the x_proj weight gradient):
  * u = silu(conv(x)) materialised per job as the operand of a cuBLAS x_proj GEMM  (njobs, E, ldu). */
