@@ -28,16 +28,24 @@ namespace umma {
 constexpr int XT = 128;            // tokens per tile = UMMA M
 constexpr int KC = 32;             // channels per K slab
 constexpr int XP = 152;            // pitch of a raw x row (144 used: 8-token aprons either side); 304 B = 19 x 16 B (odd)
-constexpr int NSX = 4;             // x / conv-tap ring slots (prefetch distance 3)
-constexpr int NSW = 5;             // W_x ring slots: one more, the tensor core reads a slot one iteration longer
+constexpr int NS = 3;              // ring depth: the x slab, the W_x slab and the u slab of one K slab share a stage
 constexpr int XPROJ_N = 48;        // dt rows (padded to 16) + B rows + C rows
 constexpr int DTN = 128;           // channels per dt_proj instruction
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 256;     // [0,64) / [64,128): x_proj accumulators of alternating tiles; [128,256): dt_proj chunk
 
 constexpr int XS_BYTES = KC * XP * 2;              // 9728
 constexpr int WX_BYTES = XPROJ_N * KC * 2;         // 3072
 constexpr int U_BYTES = KC * XT * 2;               // 8192
+constexpr int STAGE_BYTES = XS_BYTES + WX_BYTES + U_BYTES;
 constexpr int DT_BYTES = XT * 16 * 2;              // 4096
+constexpr int STG_BYTES = 32 * 32 * 2;             // one staged (32 channels x 32 tokens) block of delta
+static_assert(STAGE_BYTES % 512 == 0 && DT_BYTES % 512 == 0, "the staging blocks behind the ring must stay 512-byte aligned (64-byte swizzle)");
+
+constexpr int NCONV = 8;           // warps 0..7 convolve
+constexpr int W_PROD = 8;          // warp 8 requests the slabs (TMA)
+constexpr int W_MMA = 9;           // warp 9, lane 0 issues the x_proj MMAs
+constexpr int W_EPI = 10;          // warps 10..13 drain TMEM (one TMEM lane quarter each: warp & 3)
+constexpr int NTHREADS = 448;
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t k_stride_bytes, uint32_t mn_stride_bytes) {
   // no-swizzle canonical layout: 8 x 16-byte core matrices; "leading" byte offset = next core matrix along K, "stride" byte
@@ -105,19 +113,38 @@ template <> __device__ __forceinline__ void unpack2<__half>(uint32_t w, float& l
   lo = f.x; hi = f.y;
 }
 
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct Maps { CUtensorMap x, w_dt, w_bc, delta; };   // x slabs, W_x rows [0,R) / [R,R+32) (loads); delta blocks (stores)
+
 template <typename T>
-__global__ void __launch_bounds__(256, 2) conv_xproj_umma_kernel(cad_conv_xproj_args a, const __grid_constant__ CUtensorMap xmap) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__(NTHREADS, 2) conv_xproj_umma_kernel(cad_conv_xproj_args a, const __grid_constant__ Maps maps) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzled staging blocks need it
   const int64_t E = a.E;
   const int E128 = (int)((E + 127) / 128 * 128);
-  unsigned char* xs = smem;                                   // [NSX][KC][XP] T      raw x slabs (TMA boxes)
-  unsigned char* wxs = xs + NSX * XS_BYTES;                   // [NSW] W_x slab as a K-major UMMA operand: [k group 4][n group 6][8][16 B]
-  unsigned char* us = wxs + NSW * WX_BYTES;                   // [2]   u slab as an MN-major UMMA operand: [k group 4][token group 16][8 ch][16 B]
-  unsigned char* dts = us + 2 * U_BYTES;                      // dt rows, K-major operand: [k group 2][token group 16][8 tok][16 B]
-  unsigned char* wdts = dts + DT_BYTES;                       // W_dt, K-major operand: [k group 2][channel group E128/8][8][16 B], zero rows past E
-  float4* taps = reinterpret_cast<float4*>(wdts + (size_t)E128 * 32);   // [E] conv taps, reversed for anti-causal jobs (x 1/2 for 16-bit I/O: silu(v) = h + h tanh(h), h = v/2)
+  // stage s: [x slab: KC x XP raw samples | W_x slab, K-major operand [k group 4][n group 6][8][16 B] | u slab, MN-major operand
+  // [k group 4][token group 16][8 ch][16 B]]
+  unsigned char* stages = smem;
+  unsigned char* dts = stages + NS * STAGE_BYTES;             // dt rows, K-major operand: [k group 2][token group 16][8 tok][16 B]
+  unsigned char* stg = dts + DT_BYTES;                        // [4 warps][2] staged delta blocks (32 ch x 32 tok, 64-byte swizzle)
+  unsigned char* wdts = stg + 8 * STG_BYTES;                  // W_dt, K-major operand: [k group 2][channel group E128/8][8][16 B], zero rows past E
+  float4* taps = reinterpret_cast<float4*>(wdts + (size_t)E128 * 32);   // [E] conv taps, reversed for anti-causal jobs, x 1/2 (silu(v) = h + h tanh(h), h = v/2)
   float* cbias = reinterpret_cast<float*>(taps + E);          // [E] conv bias (same scaling)
-  __shared__ uint64_t xbar[NSX], ubar[2], accbar, dbar[2];
+  __shared__ uint64_t full[NS], x_empty[NS], u_full[NS], slab_done[NS], acc_full[2], acc_empty[2], dt_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -125,121 +152,133 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_umma_kernel(cad_conv_xproj_
   const int seq = a.seq_of_job[job], pset = a.pset_of_job[job], rev = a.rev_of_job[job];
   const int64_t L = a.L;
   const int R = (int)a.R, N = (int)a.N;
-  const T* __restrict__ wx = static_cast<const T*>(a.w_x) + (int64_t)pset * (R + 2 * N) * E;
   const T* __restrict__ wdt = static_cast<const T*>(a.w_dt) + (int64_t)pset * E * R;
-  const T* halo = a.halo ? static_cast<const T*>(a.halo) + (int64_t)job * E * 3 : nullptr;
   const T zero = io<T>::from_f(0.f);
   const int nslab = (int)(E / KC);
   const int64_t ntiles = (L + XT - 1) / XT;
   const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  const int total = my_tiles * nslab;                         // slabs this CTA walks, numbered g = 0 .. total-1 across its tiles
+  const int total = my_tiles * nslab;                         // slabs this CTA walks, g = 0 .. total-1 across its tiles
   const int64_t tile_step = (int64_t)gridDim.x * XT;
+  const uint32_t wdt_k = (uint32_t)(E128 / 8) * 128;            // K stride of the W_dt operand
 
-  // ---- one K slab into the rings: x box [c0, c0+32) x [t0-8, t0+144) by ONE bulk tensor copy (zero fill outside [0, L)),
-  //      W_x columns [c0, c0+32) as 192 16-byte pieces ---------------------------------------------------------------------
-  int pf_g = 0, pf_sl = 0;                                    // next slab to request, its index inside its tile
-  int64_t pf_t0 = (int64_t)blockIdx.x * XT;                   // and the first token of that tile
-  auto stage = [&]() {
-    if (pf_g < total) {
-      const int c0 = pf_sl * KC;
-      if (tid == 0) {
-        uint64_t* bar = &xbar[pf_g % NSX];
-        mbar_expect_tx(bar, XS_BYTES);
-        tma_load_3d(xs + (pf_g % NSX) * XS_BYTES, &xmap, (int)(pf_t0 - 8), c0, seq, bar);
-      }
-      if (tid < XPROJ_N * (KC / 8)) {                        // 192 16-byte pieces: (operand row n, k group)
-        const int n = tid >> 2, kg = tid & 3;
-        const int src = n < 16 ? (n < R ? n : -1) : n - 16 + R;      // dt rows padded to 16: rows [R, 16) stay zero
-        if (src >= 0)
-          cp_async16(wxs + (pf_g % NSW) * WX_BYTES + kg * (XPROJ_N / 8 * 128) + (n >> 3) * 128 + (n & 7) * 16,
-                     wx + (int64_t)src * E + c0 + 8 * kg);
-      }
-      ++pf_g;
-      if (++pf_sl == nslab) { pf_sl = 0; pf_t0 += tile_step; }
-    }
-    cp_async_commit();
-  };
-
-  // ---- set-up: barriers, TMEM, zero rows of the W_x ring, resident W_dt and conv taps ------------------------------------
+  // ---- set-up (all warps): barriers, TMEM, zero dt rows of the W_x slabs, resident W_dt and conv taps ---------------------
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NSX; ++i) mbar_init(&xbar[i], 1);
-    mbar_init(&ubar[0], 1); mbar_init(&ubar[1], 1); mbar_init(&accbar, 1); mbar_init(&dbar[0], 1); mbar_init(&dbar[1], 1);
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&x_empty[i], NCONV); mbar_init(&u_full[i], NCONV); mbar_init(&slab_done[i], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1); mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+    mbar_init(&dt_full, 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w_dt)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.w_bc)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.delta)) : "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (R < 16)
-    for (int i = tid; i < NSW * WX_BYTES / 16; i += 256) reinterpret_cast<uint4*>(wxs)[i] = make_uint4(0, 0, 0, 0);
-  const uint32_t wdt_k = (uint32_t)(E128 / 8) * 128;            // K stride of the W_dt operand
-  {
-    if (R == 16) {
-      for (int i = tid; i < E128 * 2; i += 256) {
-        const int ch = i >> 1, kg = i & 1;
-        *reinterpret_cast<uint4*>(wdts + kg * wdt_k + (ch >> 3) * 128 + (ch & 7) * 16) =
-            ch < E ? __ldg(reinterpret_cast<const uint4*>(wdt + (int64_t)ch * 16 + 8 * kg)) : make_uint4(0, 0, 0, 0);
-      }
-    } else {
-      for (int i = tid; i < E128 * 16; i += 256) {
-        const int ch = i >> 4, r = i & 15;
-        *reinterpret_cast<T*>(wdts + (r >> 3) * wdt_k + (ch >> 3) * 128 + (ch & 7) * 16 + (r & 7) * 2) =
-            (r < R && ch < E) ? wdt[(int64_t)ch * R + r] : zero;
-      }
+  if (R < 16)                                                  // operand rows [R, 16) of every k group: never written by a copy
+    for (int i = tid; i < NS * (WX_BYTES / 16); i += NTHREADS) {
+      const int st = i / (WX_BYTES / 16), v = i - st * (WX_BYTES / 16);
+      reinterpret_cast<uint4*>(stages + st * STAGE_BYTES + XS_BYTES)[v] = make_uint4(0, 0, 0, 0);
     }
-    const float sc = sizeof(T) == 2 ? 0.5f : 1.0f;
-    for (int ch = tid; ch < (int)E; ch += 256) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(a.conv_w) + (int64_t)pset * E + ch);
-      taps[ch] = rev ? make_float4(sc * w.w, sc * w.z, sc * w.y, sc * w.x) : make_float4(sc * w.x, sc * w.y, sc * w.z, sc * w.w);
-      cbias[ch] = sc * a.conv_b[(int64_t)pset * E + ch];
+  if (R == 16) {
+    for (int i = tid; i < E128 * 2; i += NTHREADS) {
+      const int ch = i >> 1, kg = i & 1;
+      *reinterpret_cast<uint4*>(wdts + kg * wdt_k + (ch >> 3) * 128 + (ch & 7) * 16) =
+          ch < E ? __ldg(reinterpret_cast<const uint4*>(wdt + (int64_t)ch * 16 + 8 * kg)) : make_uint4(0, 0, 0, 0);
+    }
+  } else {
+    for (int i = tid; i < E128 * 16; i += NTHREADS) {
+      const int ch = i >> 4, r = i & 15;
+      *reinterpret_cast<T*>(wdts + (r >> 3) * wdt_k + (ch >> 3) * 128 + (ch & 7) * 16 + (r & 7) * 2) =
+          (r < R && ch < E) ? wdt[(int64_t)ch * R + r] : zero;
     }
   }
-  __syncthreads();                                           // barriers initialised, zero rows written before any copy lands
-  stage(); stage(); stage();
-  cp_async_wait<2>();
-  proxy_fence();
+  for (int ch = tid; ch < (int)E; ch += NTHREADS) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(a.conv_w) + (int64_t)pset * E + ch);
+    taps[ch] = rev ? make_float4(0.5f * w.w, 0.5f * w.z, 0.5f * w.y, 0.5f * w.x) : make_float4(0.5f * w.x, 0.5f * w.y, 0.5f * w.z, 0.5f * w.w);
+    cbias[ch] = 0.5f * a.conv_b[(int64_t)pset * E + ch];
+  }
+  proxy_fence();                                               // W_dt / zero rows (generic stores) -> visible to the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t idesc_x = instr_desc<T>(XT, XPROJ_N, 1);
-  const uint32_t idesc_dt = instr_desc<T>(128, XT, 0);
-  const int q = warp & 3, half = warp >> 2;                  // TMEM lane quarter this warp may read; column half it takes
-  const uint32_t tlane = (uint32_t)(32 * q) << 16;
-  uint32_t nuse_d0 = 0, nuse_d1 = 0;                          // completed-phase counters of dbar[0], dbar[1]
-  int sl = 0, it = 0;
-  int64_t t0 = (int64_t)blockIdx.x * XT;
-  const int tg = 4 * q + (lane >> 3);                          // conv: my token group 0..15 and channel inside a group of 8
-  const int cl = lane & 7;
 
-  for (int g = 0; g < total; ++g) {
-    const int buf = g & 1;
-    // u[buf] and W_x slot (g-2) % NSW are free once the MMAs of slab g-2 have completed
-    if (g >= 2) mbar_wait_wd(&ubar[buf], (uint32_t)(((g >> 1) - 1) & 1));
-    stage();                                                   // slab g+3 -> x slot (g-1) % NSX, read for the last time before the previous barrier
-    mbar_wait_wd(&xbar[g % NSX], (uint32_t)((g / NSX) & 1));
-    unsigned char* xb = xs + (g % NSX) * XS_BYTES;
-    if (halo && ((!rev && t0 == 0) || (rev && t0 + XT >= L))) {  // shard hook: the 3 samples that logically precede the shard
-      if (tid < KC * 3) {
-        const int ch = tid / 3, k = tid - ch * 3;
-        const int64_t te = rev ? L + k : (int64_t)k - 3;        // physical position just outside the sequence
-        const int64_t tau = rev ? L - 1 - te : te;              // logical time -3 .. -1
-        reinterpret_cast<T*>(xb)[ch * XP + (int)(te - (t0 - 8))] = halo[((int64_t)sl * KC + ch) * 3 + tau + 3];
+  if (warp == W_PROD) {
+    // ===== slab requests: x box [c0, c0+32) x [t0-8, t0+144) (zero fill outside [0, L)), W_x columns [c0, c0+32) as
+    //       2 x 4 boxes of 8 columns: dt rows -> operand rows [0, R), B / C rows -> operand rows [16, 48) ====================
+    int s = 0, ph = 0, sl = 0;
+    int64_t t0 = (int64_t)blockIdx.x * XT;
+    const uint32_t bytes = XS_BYTES + (uint32_t)(R + 32) * KC * 2;
+    for (int g = 0; g < total; ++g) {
+      if (g >= NS) { mbar_wait_wd(&x_empty[s], ph ^ 1); mbar_wait_wd(&slab_done[s], ph ^ 1); }
+      unsigned char* st = stages + s * STAGE_BYTES;
+      if (lane == 0) mbar_expect_tx(&full[s], bytes);
+      __syncwarp();
+      const int c0 = sl * KC;
+      if (lane == 0) {
+        tma_load_3d(st, &maps.x, (int)(t0 - 8), c0, seq, &full[s]);
+      } else if (lane <= 4) {
+        const int kg = lane - 1;
+        tma_load_2d(st + XS_BYTES + kg * (XPROJ_N / 8 * 128), &maps.w_dt, c0 + 8 * kg, pset * (R + 32), &full[s]);
+      } else if (lane <= 8) {
+        const int kg = lane - 5;
+        tma_load_2d(st + XS_BYTES + kg * (XPROJ_N / 8 * 128) + 256, &maps.w_bc, c0 + 8 * kg, pset * (R + 32) + R, &full[s]);
       }
-      __syncthreads();
+      if (++sl == nslab) { sl = 0; t0 += tile_step; }
+      if (++s == NS) { s = 0; ph ^= 1; }
     }
-    // ---- conv + SiLU: this thread's two (channel, 8-token vector) pieces of the slab -----------------------------------
-    {
-      unsigned char* ub = us + buf * U_BYTES;
+  } else if (warp == W_MMA) {
+    // ===== x_proj: D1[128 tokens x 48] += u^T . W_x^T, accumulator of tile `it` in TMEM columns [64 (it & 1), +48) =========
+    const uint32_t idesc_x = instr_desc<T>(XT, XPROJ_N, 1);
+    int s = 0, ph = 0, sl = 0, it = 0;
+    for (int g = 0; g < total; ++g) {
+      if (sl == 0 && it >= 2) mbar_wait_wd(&acc_empty[it & 1], (uint32_t)(((it >> 1) - 1) & 1));
+      mbar_wait_wd(&full[s], ph);
+      mbar_wait_wd(&u_full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t wa = smem_u32(stages + s * STAGE_BYTES + XS_BYTES), ua = wa + WX_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < KC / 16; ++ks)
+          mma_f16(tmem + (uint32_t)(64 * (it & 1)), smem_desc(ua + ks * 2 * (XT / 8 * 128), XT / 8 * 128, 128),
+                  smem_desc(wa + ks * 2 * (XPROJ_N / 8 * 128), XPROJ_N / 8 * 128, 128), idesc_x, (sl | ks) ? 1u : 0u);
+        mma_commit(&slab_done[s]);
+        if (sl == nslab - 1) mma_commit(&acc_full[it & 1]);
+      }
+      __syncwarp();
+      if (++sl == nslab) { sl = 0; ++it; }
+      if (++s == NS) { s = 0; ph ^= 1; }
+    }
+  } else if (warp < NCONV) {
+    // ===== conv + SiLU: per slab this thread's two (channel, 8-token vector) pieces ==========================================
+    const int q = warp & 3, half = warp >> 2;
+    const int tg = 4 * q + (lane >> 3);                        // token group 0..15
+    const int cl = lane & 7;                                   // channel inside a group of 8
+    const T* halo = a.halo ? static_cast<const T*>(a.halo) + (int64_t)job * E * 3 : nullptr;
+    int s = 0, ph = 0, sl = 0;
+    int64_t t0 = (int64_t)blockIdx.x * XT;
+    for (int g = 0; g < total; ++g) {
+      unsigned char* st = stages + s * STAGE_BYTES;
+      mbar_wait_wd(&full[s], ph);
+      uint4 xr[2][3];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint4* xv = reinterpret_cast<const uint4*>(st + ((8 * (2 * half + i) + cl) * XP + 8 * tg) * 2);   // x[t-8 .. t+15], t = t0 + 8 tg
+        xr[i][0] = xv[0]; xr[i][1] = xv[1]; xr[i][2] = xv[2];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&x_empty[s]);                 // my warp holds its samples in registers
+      if (g >= NS) mbar_wait_wd(&slab_done[s], ph ^ 1);        // the MMAs that read u[s] one round ago have completed
+      const bool edge = halo && ((!rev && t0 == 0) || (rev && t0 + XT >= L));
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int kg = 2 * half + i;                           // channel group 0..3
-        const int ch = 8 * kg + cl;
-        const float4 cw = taps[sl * KC + ch];
-        const float cb = cbias[sl * KC + ch];
-        const uint4* xv = reinterpret_cast<const uint4*>(xb + (ch * XP + 8 * tg) * 2);   // x[t-8 .. t+15], t = t0 + 8 tg
-        const uint4 r0 = xv[0], r1 = xv[1], r2 = xv[2];
+        const int ch = sl * KC + 8 * kg + cl;
+        const float4 cw = taps[ch];
+        const float cb = cbias[ch];
+        const uint4 r0 = xr[i][0], r1 = xr[i][1], r2 = xr[i][2];
         // 12-sample window so that output e reads win[e+1 .. e+4] in BOTH directions: causal jobs x[t-4 .. t+7] with taps
         // (w0..w3), anti-causal jobs x[t-1 .. t+10] with the taps stored reversed (one uniform branch per piece)
         float win[12];
@@ -254,50 +293,52 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_umma_kernel(cad_conv_xproj_
           unpack2<T>(r1.z, win[5], win[6]); unpack2<T>(r1.w, win[7], win[8]);
           unpack2<T>(r2.x, win[9], win[10]); unpack2<T>(r2.y, win[11], skip);
         }
+        if (edge) {                                            // shard hook: the 3 samples that logically precede the shard
+          const int64_t tw = t0 + 8 * tg + (rev ? -1 : -4);     // physical position of win[0]
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {
+            const int64_t te = tw + k;
+            const int64_t tau = rev ? L - 1 - te : te;          // logical time
+            if (tau >= -3 && tau < 0) win[k] = io<T>::to_f(halo[(int64_t)ch * 3 + tau + 3]);
+          }
+        }
         uint4 outv;
         uint32_t* o = reinterpret_cast<uint32_t*>(&outv);
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {                       // outputs t+e, t+e+1
+        for (int e = 0; e < 8; e += 2) {                       // outputs t+e, t+e+1 (taps pre-scaled: c = v/2)
           float c0v = cb + cw.x * win[e + 1] + cw.y * win[e + 2] + cw.z * win[e + 3] + cw.w * win[e + 4];
           float c1v = cb + cw.x * win[e + 2] + cw.y * win[e + 3] + cw.z * win[e + 4] + cw.w * win[e + 5];
-          if constexpr (sizeof(T) == 2) {                      // taps pre-scaled: c = v/2
-            c0v = fmaf(c0v, tanh_approx(c0v), c0v);
-            c1v = fmaf(c1v, tanh_approx(c1v), c1v);
-          } else {
-            c0v = silu(c0v); c1v = silu(c1v);
-          }
+          c0v = fmaf(c0v, tanh_approx(c0v), c0v);
+          c1v = fmaf(c1v, tanh_approx(c1v), c1v);
           o[e >> 1] = pack2<T>(c0v, c1v);
         }
         // core matrix (k group kg, token group tg), row = channel within the group: a quarter-warp writes 128 contiguous bytes
-        *reinterpret_cast<uint4*>(ub + kg * (XT / 8 * 128) + tg * 128 + cl * 16) = outv;
+        *reinterpret_cast<uint4*>(st + XS_BYTES + WX_BYTES + kg * (XT / 8 * 128) + tg * 128 + cl * 16) = outv;
       }
+      proxy_fence();                                           // my u stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&u_full[s]);
+      if (++sl == nslab) { sl = 0; t0 += tile_step; }
+      if (++s == NS) { s = 0; ph ^= 1; }
     }
-    cp_async_wait<2>();                                        // W_x of slab g+1 has landed (g+2, g+3 may still be in flight)
-    proxy_fence();                                             // my u stores / W_x cp.async data -> visible to the tensor core
-    tc_fence_before();                                         // (and my TMEM reads of the previous tile's epilogue are done)
-    __syncthreads();
-    if (tid == 0) {
+  } else if (warp >= W_EPI) {
+    // ===== tile epilogue: x_dbl out of TMEM, dt_proj, delta out ================================================================
+    const int q = warp & 3, we = warp - W_EPI;                 // my TMEM lane quarter; my staging buffers
+    const uint32_t tlane = (uint32_t)(32 * q) << 16;
+    const uint32_t idesc_dt = instr_desc<T>(128, XT, 0);
+    const int nchunk = E128 / DTN;
+    unsigned char* mystg = stg + we * 2 * STG_BYTES;
+    uint32_t ndt = 0, nstg = 0;                                // dt_full phases consumed; staged blocks written
+    int64_t t0 = (int64_t)blockIdx.x * XT;
+    for (int it = 0; it < my_tiles; ++it, t0 += tile_step) {
+      mbar_wait_wd(&acc_full[it & 1], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const uint32_t ua = smem_u32(us + buf * U_BYTES), wa = smem_u32(wxs + (g % NSW) * WX_BYTES);
-#pragma unroll
-      for (int ks = 0; ks < KC / 16; ++ks)
-        mma_f16(tmem, smem_desc(ua + ks * 2 * (XT / 8 * 128), XT / 8 * 128, 128),
-                smem_desc(wa + ks * 2 * (XPROJ_N / 8 * 128), XPROJ_N / 8 * 128, 128), idesc_x, (sl | ks) ? 1u : 0u);
-      mma_commit(&ubar[buf]);
-      if (sl == nslab - 1) mma_commit(&accbar);
-    }
-    if (++sl != nslab) continue;
-
-    // ================= tile epilogue ======================================================================================
-    sl = 0;
-    mbar_wait_wd(&accbar, (uint32_t)(it & 1));
-    tc_fence_after();
-    {
-      // warps 0-3: dt columns [0,16) -> io dtype -> dt operand; B columns [16,32) -> bc rows [0,16).  warps 4-7: C columns.
+      const uint32_t acc = tmem + tlane + (uint32_t)(64 * (it & 1));
       const int64_t t = t0 + 32 * q + lane;                     // my token (TMEM lane)
-      uint32_t v[16];
-      if (half == 0) {
-        tmem_ld16(tmem + tlane + 0, v);
+      {
+        uint32_t v[16], w[16];
+        tmem_ld16(acc, v);                                      // dt columns [0,16) -> io dtype -> dt operand (K-major rows = tokens)
+        tmem_ld16(acc + 16, w);                                 // B columns
         tmem_ld_wait();
         uint4 lo, hi;
         lo.x = pack2<T>(__uint_as_float(v[0]), __uint_as_float(v[1]));   lo.y = pack2<T>(__uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -307,76 +348,95 @@ __global__ void __launch_bounds__(256, 2) conv_xproj_umma_kernel(cad_conv_xproj_
         const int row = 32 * q + lane;
         *reinterpret_cast<uint4*>(dts + (row >> 3) * 128 + (row & 7) * 16) = lo;
         *reinterpret_cast<uint4*>(dts + (XT / 8 * 128) + (row >> 3) * 128 + (row & 7) * 16) = hi;
-      }
-      tmem_ld16(tmem + tlane + 16 + 16 * half, v);
-      tmem_ld_wait();
-      const bool live = t < L;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) if (!live) v[j] = 0u;
-      if (t < a.ldbc) {
-        float* dst = a.bc + ((int64_t)job * 2 * N + 16 * half) * a.ldbc + t;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dst[(int64_t)j * a.ldbc] = __uint_as_float(v[j]);
-      }
-      if (a.bcT && t < a.ldT) {
-        uint4* dT = reinterpret_cast<uint4*>(a.bcT + ((int64_t)job * a.ldT + t) * (2 * N) + 16 * half);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dT[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-    }
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();                                           // dt operand complete; x_proj accumulator columns free
-    // dt_proj, channels on the TMEM lanes: D2[128 channels x 128 tokens] = W_dt[chunk] . dt^T, so that a thread reads 32
-    // consecutive tokens of ONE channel row and stores them as four 16-byte vectors
-    const int nchunk = E128 / DTN;
-    auto issue_dt = [&](int c) {                               // chunk c -> TMEM buffer c & 1
-      tc_fence_after();
-      mma_f16(tmem + (uint32_t)((c & 1) * XT), smem_desc(smem_u32(wdts) + (uint32_t)(c * DTN / 8) * 128, wdt_k, 128),
-              smem_desc(smem_u32(dts), XT / 8 * 128, 128), idesc_dt, 0u);
-      mma_commit(&dbar[c & 1]);
-    };
-    if (tid == 0) { issue_dt(0); if (nchunk > 1) issue_dt(1); }
-    for (int c = 0; c < nchunk; ++c) {
-      if (c & 1) { mbar_wait_wd(&dbar[1], nuse_d1 & 1); ++nuse_d1; } else { mbar_wait_wd(&dbar[0], nuse_d0 & 1); ++nuse_d0; }
-      tc_fence_after();
-      const int ch = c * DTN + 32 * q + lane;                   // my channel (TMEM lane)
-      T* __restrict__ drow = static_cast<T*>(a.delta) + ((int64_t)job * E + ch) * a.ldd + t0 + 64 * half;
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {                    // my 64 tokens, 32 at a time
-        uint32_t v[32];
-        tmem_ld32(tmem + tlane + (uint32_t)((c & 1) * XT + 64 * half + cc), v);
+        tmem_ld16(acc + 32, v);                                 // C columns
         tmem_ld_wait();
-        if (ch < E) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[it & 1]);        // the accumulator may be overwritten by tile it + 2
+        const bool live = t < L;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t t = t0 + 64 * half + cc + 8 * j;
-            if (t < a.ldd)
-              *reinterpret_cast<uint4*>(drow + cc + 8 * j) =
-                  make_uint4(pack2<T>(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                             pack2<T>(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                             pack2<T>(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                             pack2<T>(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-          }
+        for (int j = 0; j < 16; ++j) { if (!live) { v[j] = 0u; w[j] = 0u; } }
+        if (t < a.ldbc) {
+          float* dst = a.bc + (int64_t)job * 2 * N * a.ldbc + t;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dst[(int64_t)j * a.ldbc] = __uint_as_float(w[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dst[(int64_t)(16 + j) * a.ldbc] = __uint_as_float(v[j]);
+        }
+        if (a.bcT && t < a.ldT) {
+          uint4* dT = reinterpret_cast<uint4*>(a.bcT + ((int64_t)job * a.ldT + t) * (2 * N));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dT[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dT[4 + j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
-      if (c + 2 < nchunk) {                                    // hand the buffer back for chunk c + 2
+      // dt_proj, channels on the TMEM lanes: D2[128 channels x 128 tokens] = W_dt[chunk] . dt^T in TMEM columns [128, 256): a
+      // thread reads 32 consecutive tokens of ONE delta row; the warp stages (32 channels x 32 tokens) and one lane stores the
+      // block with a bulk tensor copy (full 64-byte row segments leave the SM without touching the LSU)
+      for (int c = 0; c < nchunk; ++c) {
+        proxy_fence();                                         // (c == 0) my dt operand rows -> visible to the tensor core
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) issue_dt(c + 2);
+        asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps: operand complete / chunk buffer drained
+        if (we == 0 && lane == 0) {
+          tc_fence_after();
+          mma_f16(tmem + 128u, smem_desc(smem_u32(wdts) + (uint32_t)(c * DTN / 8) * 128, wdt_k, 128),
+                  smem_desc(smem_u32(dts), XT / 8 * 128, 128), idesc_dt, 0u);
+          mma_commit(&dt_full);
+        }
+        mbar_wait_wd(&dt_full, ndt & 1); ++ndt;
+        tc_fence_after();
+        const int ch0 = c * DTN + 32 * q;                       // my warp's 32 channels (TMEM lanes)
+#pragma unroll 1
+        for (int cc = 0; cc < XT; cc += 32) {                  // 32 tokens at a time
+          uint32_t v[32];
+          tmem_ld32(tmem + tlane + 128u + (uint32_t)cc, v);
+          tmem_ld_wait();
+          unsigned char* blk = mystg + (nstg & 1) * STG_BYTES;
+          if (lane == 0) bulk_wait_read<1>();                  // the store that last read this buffer has drained it
+          __syncwarp();
+          // row = my channel (64 bytes = 32 tokens), 16-byte chunk j at j ^ ((row >> 1) & 3): the 64-byte swizzle of the map
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(blk + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pack2<T>(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                           pack2<T>(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                           pack2<T>(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                           pack2<T>(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+          proxy_fence();
+          __syncwarp();
+          if (lane == 0) {                                      // rows >= E and tokens >= ldd are clipped by the tensor map
+            tma_store_3d(&maps.delta, blk, (int)(t0 + cc), ch0, job);
+            bulk_commit();
+          }
+          ++nstg;
+        }
       }
     }
-    // the next tile's first MMA is issued after the next __syncthreads (tc_fence_before precedes it): TMEM reads are ordered
-    ++it;
-    t0 += tile_step;
+    if (lane == 0) bulk_wait_read<0>();
   }
 
-  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
+}  // namespace umma
+}  // namespace cad
+
+namespace cad {
+namespace umma {
+static int encode_map(CUtensorMap* m, int is_bf16, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return -1; }
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cad_conv_xproj_umma_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+  return 0;
+}
 }  // namespace umma
 }  // namespace cad
 
@@ -397,24 +457,36 @@ extern "C" int cad_conv_xproj_umma_fwd(const cad_conv_xproj_args* a, void* strea
   CAD_REQUIRE(aligned16(a->xz) && aligned16(a->w_x) && aligned16(a->delta) && aligned16(a->conv_w) &&
               (a->R != 16 || aligned16(a->w_dt)), "cad_conv_xproj_umma_fwd: alignment");
   CAD_REQUIRE(!a->bcT || (aligned16(a->bcT) && a->ldT >= a->L), "cad_conv_xproj_umma_fwd: bcT must be 16-byte aligned with ldT >= L");
-  CAD_REQUIRE(a->L < (int64_t)1 << 31, "cad_conv_xproj_umma_fwd: sequence too long for 32-bit tensor-map coordinates");
+  CAD_REQUIRE(a->L < ((int64_t)1 << 31) - 1024, "cad_conv_xproj_umma_fwd: sequence too long for 32-bit tensor-map coordinates");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  // x half of xz as a (L tokens, 2E rows, nseq) tensor: one box = 152 tokens x 32 channels; tokens outside [0, L) read as zero
-  CUtensorMap xmap;
+  const int bf = a->io_dtype == CAD_BF16;
+  const cuuint64_t E = (cuuint64_t)a->E, R = (cuuint64_t)a->R;
+  Maps maps;
   {
-    EncodeTiledFn enc = encode_tiled_fn();
-    CAD_REQUIRE(enc, "cuTensorMapEncodeTiled not available from the driver");
-    const cuuint64_t dims[3] = {(cuuint64_t)a->L, (cuuint64_t)(2 * a->E), (cuuint64_t)a->nseq};
-    const cuuint64_t strides[2] = {(cuuint64_t)a->ldxz * 2, (cuuint64_t)a->ldxz * 2 * 2 * (cuuint64_t)a->E};
+    // x half of xz as (L tokens, 2E rows, nseq): one box = 152 tokens x 32 channels; tokens outside [0, L) read as zero
+    const cuuint64_t dims[3] = {(cuuint64_t)a->L, 2 * E, (cuuint64_t)a->nseq};
+    const cuuint64_t strides[2] = {(cuuint64_t)a->ldxz * 2, (cuuint64_t)a->ldxz * 2 * 2 * E};
     const cuuint32_t box[3] = {(cuuint32_t)XP, (cuuint32_t)KC, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&xmap, a->io_dtype == CAD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
-                     const_cast<void*>(a->xz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cad_conv_xproj_umma_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    if (encode_map(&maps.x, bf, a->xz, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+  }
+  {
+    // W_x as (E columns, rows): boxes of 8 columns x R rows (dt rows) and 8 columns x 32 rows (B / C rows); the row count is only
+    // a clipping bound (the number of parameter sets is not part of the argument block): coordinates come from the job tables
+    const cuuint64_t dims[2] = {E, (R + 32) * 4096};
+    const cuuint64_t strides[1] = {E * 2};
+    const cuuint32_t box_dt[2] = {8, (cuuint32_t)R}, box_bc[2] = {8, 32};
+    if (encode_map(&maps.w_dt, bf, a->w_x, 2, dims, strides, box_dt, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    if (encode_map(&maps.w_bc, bf, a->w_x, 2, dims, strides, box_bc, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+  }
+  {
+    // delta as (ldd tokens, E rows, njobs): stores of (32 tokens x 32 rows) blocks staged with the 64-byte swizzle
+    const cuuint64_t dims[3] = {(cuuint64_t)a->ldd, E, (cuuint64_t)a->njobs};
+    const cuuint64_t strides[2] = {(cuuint64_t)a->ldd * 2, (cuuint64_t)a->ldd * 2 * E};
+    const cuuint32_t box[3] = {32, 32, 1};
+    if (encode_map(&maps.delta, bf, a->delta, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
   }
   const int64_t E128 = (a->E + 127) / 128 * 128;
-  const size_t smem = (size_t)NSX * XS_BYTES + NSW * WX_BYTES + 2 * U_BYTES + DT_BYTES + (size_t)E128 * 32 + (size_t)a->E * 20;
+  const size_t smem = 1024 + (size_t)NS * STAGE_BYTES + DT_BYTES + 8 * STG_BYTES + (size_t)E128 * 32 + (size_t)a->E * 20;
   const int64_t ntiles = (a->L + XT - 1) / XT;
   const int sms = cad_sm_count();
   CAD_REQUIRE(sms > 0, "cad_conv_xproj_umma_fwd: no CUDA device");
@@ -424,12 +496,12 @@ extern "C" int cad_conv_xproj_umma_fwd(const cad_conv_xproj_args* a, void* strea
   if (per_job < 1) per_job = 1;
   dim3 grid((unsigned)per_job, (unsigned)a->njobs);
   cudaError_t e;
-  if (a->io_dtype == CAD_BF16) {
+  if (bf) {
     e = cudaFuncSetAttribute(conv_xproj_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_xproj_umma_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(*a, xmap);
+    if (e == cudaSuccess) conv_xproj_umma_kernel<__nv_bfloat16><<<grid, NTHREADS, smem, stream>>>(*a, maps);
   } else {
     e = cudaFuncSetAttribute(conv_xproj_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) conv_xproj_umma_kernel<__half><<<grid, 256, smem, stream>>>(*a, xmap);
+    if (e == cudaSuccess) conv_xproj_umma_kernel<__half><<<grid, NTHREADS, smem, stream>>>(*a, maps);
   }
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   CAD_LAUNCH_CHECK();
