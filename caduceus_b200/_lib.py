@@ -149,7 +149,6 @@ SYMBOLS = {
     "cad_bimamba_scan_fixup": (C.c_int, [C.POINTER(ScanFixupArgs), _p]),
     "cad_conv_silu_bwd": (C.c_int, [C.POINTER(ConvBwdArgs), _p]),
     "cad_conv_xproj_fwd": (C.c_int, [C.POINTER(ConvXprojArgs), _p]),
-    "cad_conv_xproj_umma_fwd": (C.c_int, [C.POINTER(ConvXprojArgs), _p]),
     "cad_bimamba_scan_adjoint": (C.c_int, [C.POINTER(ScanAdjointArgs), _p]),
     "cad_bc_transpose": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p]),
     "cad_seg_carry": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),

@@ -19,8 +19,6 @@ LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py report
 # The two forward-scan kernels are described at cad_scan_fwd_args.variant in include/caduceus_b200.h and measured in DESIGN.md §4.
 SCAN_VARIANT = int(os.environ.get("CAD_SCAN_VARIANT", "0"))         # 0 = choose per call (choose_scan_variant); 3 / 20 = force
 SCAN_NSEG = int(os.environ.get("CAD_SCAN_NSEG", "0"))               # variant 20: time segments per job (0 = default_nseg)
-# conv_xproj kernel: "umma" = tcgen05 tensor cores + TMEM (csrc/xproj_umma.cu), "mma" = warp-level mma.sync (csrc/xproj.cu)
-XPROJ_KERNEL = os.environ.get("CAD_XPROJ_KERNEL", "mma")
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 
 
@@ -256,14 +254,13 @@ def conv_silu(xz, conv_w4, conv_b, jobs, L, halo=None):
 
 def conv_xproj_supported(xz, N, R):
     E = xz.shape[1] // 2
-    return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 1024
+    return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 2048
 
 
-def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=False, kernel=None):
-    """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores: returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc) fp32)
-    without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.
-    want_bcT: also return the B / C rows token-major, (njobs, ceil256(L), 2N) fp32 — what scan variant 20 reads.
-    kernel: "umma" (tcgen05 + TMEM) or "mma" (mma.sync); None = XPROJ_KERNEL."""
+def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=False):
+    """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores (tcgen05 + TMEM): returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc)
+    fp32) without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.
+    want_bcT: also return the B / C rows token-major, (njobs, ceil256(L), 2N) fp32 — what scan variant 20 reads."""
     lib = _lib.load()
     seq, pset, rev = jobs
     nseq, twoE, ld = xz.shape
@@ -284,13 +281,7 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=Fals
         if Lp > L128:
             bcT[:, L128:].zero_()                 # rows no 128-token tile of the kernel covers
         a.bcT, a.ldT = _ptr(bcT), Lp
-    kernel = kernel or XPROJ_KERNEL
-    if kernel == "umma":
-        _lib.check(lib.cad_conv_xproj_umma_fwd(C.byref(a), _stream()), "cad_conv_xproj_umma_fwd")
-    elif kernel == "mma":
-        _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
-    else:
-        raise ValueError(f"conv_xproj: unknown kernel {kernel!r}")
+    _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
     _launched()
     return (delta, bc, bcT) if want_bcT else (delta, bc)
 

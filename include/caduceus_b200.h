@@ -288,12 +288,15 @@ typedef struct {
 } cad_conv_bwd_args;
 int cad_conv_silu_bwd(const cad_conv_bwd_args* a, void* stream);
 
-/* ---- fused conv + SiLU -> x_proj -> dt_proj (tensor cores, 16-bit I/O): produces exactly the operands of
- *      cad_bimamba_scan_fwd without materialising u = silu(conv(x)).  Replaces causal_conv1d_fwd + the x_proj and
- *      dt_proj GEMMs of upstream's mamba_inner_fn.
- *        w_x (P, R+2N, E), w_dt (P, E, R) in the io dtype;  delta (njobs, E, ldd) io dtype;
- *        bc (njobs, 2N, ldbc) fp32, written for every column < ldbc (zeros beyond L).
- *      Constraints: io dtype f16/bf16, N == 16, R <= 16, E % 64 == 0; otherwise use cad_conv_silu_fwd + GEMMs.   */
+/* ---- fused conv + SiLU -> x_proj -> dt_proj on the 5th-generation tensor cores (16-bit I/O): produces exactly the operands
+ *      of cad_bimamba_scan_fwd without materialising u = silu(conv(x)).  Replaces causal_conv1d_fwd + the x_proj and dt_proj
+ *      GEMMs of upstream's mamba_inner_fn.  csrc/xproj.cu: tcgen05.mma issued by one thread per CTA,
+ *      accumulators in tensor memory read back with tcgen05.ld, x / W_x slabs by TMA loads, delta by TMA stores; persistent
+ *      warp-specialised CTAs, two per SM.
+ *        w_x (P, R+2N, E), w_dt (P, E, R) in the io dtype;  delta (njobs, E, ldd) io dtype, written for every column < ldd;
+ *        bc (njobs, 2N, ldbc) fp32, written for every column < min(ldbc, ceil128(L)) (zeros beyond L).
+ *      Constraints: io dtype f16/bf16, N == 16, R <= 16, E % 64 == 0, E <= 2048, ldxz % 8 == 0, ldd % 8 == 0; otherwise use
+ *      cad_conv_silu_fwd + GEMMs.                                                                                          */
 typedef struct {
   const void* xz; const void* w_x; const void* w_dt;
   const float* conv_w; const float* conv_b;
@@ -308,10 +311,6 @@ typedef struct {
   int64_t ldT;              /* rows per job of bcT (ceil256(L)) */
 } cad_conv_xproj_args;
 int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
-/* The same operator with both projections on the 5th-generation tensor cores (tcgen05.mma issued by one thread per CTA,
- * accumulators in tensor memory, read back with tcgen05.ld; csrc/xproj_umma.cu): persistent CTAs, two per SM.  Same
- * argument block and outputs; d_inner may be any multiple of 64 up to 2048 and ldd need not be a multiple of 16.      */
-int cad_conv_xproj_umma_fwd(const cad_conv_xproj_args* a, void* stream);
 
 /* unfused helper (fp32 I/O and the training path, which needs u for the x_proj weight gradient):
  * u = silu(conv(x)) materialised per job as the operand of a cuBLAS x_proj GEMM  (njobs, E, ldu). */

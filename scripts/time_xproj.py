@@ -17,7 +17,6 @@ ap.add_argument("--L", type=int, default=131072)
 ap.add_argument("--E", type=int, default=512)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--bcT", type=int, default=1)
-ap.add_argument("--kernel", default=None, help="umma | mma (default: functional.XPROJ_KERNEL)")
 a = ap.parse_args()
 dev, L, E, N, R = "cuda", a.L, a.E, 16, 16
 nstrand = 2 if a.model == "ps" else 1
@@ -30,15 +29,15 @@ w_dt = (torch.randn(2, E, R, generator=g) * R ** -0.5).to(dev).bfloat16()
 conv_w4 = (0.5 * torch.randn(2, E, 4, generator=g)).to(dev)
 conv_b = (0.1 * torch.randn(2, E, generator=g)).to(dev)
 for _ in range(3):
-    CF.conv_xproj(sets[0], w_x, w_dt, conv_w4, conv_b, jobs, L, want_bcT=bool(a.bcT), kernel=a.kernel)
+    CF.conv_xproj(sets[0], w_x, w_dt, conv_w4, conv_b, jobs, L, want_bcT=bool(a.bcT))
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for i in range(a.iters):
-    CF.conv_xproj(sets[i & 1], w_x, w_dt, conv_w4, conv_b, jobs, L, want_bcT=bool(a.bcT), kernel=a.kernel)
+    CF.conv_xproj(sets[i & 1], w_x, w_dt, conv_w4, conv_b, jobs, L, want_bcT=bool(a.bcT))
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
 bytes_ = njobs * E * L * 2 * 2 + njobs * 2 * N * L * 4 * (2 if a.bcT else 1)
-print(json.dumps({"kernel": "conv_xproj_" + (a.kernel or CF.XPROJ_KERNEL), "model": a.model, "L": L, "E": E, "bcT": bool(a.bcT), "ms_per_launch": round(ms, 4),
+print(json.dumps({"kernel": "conv_xproj_umma_kernel", "model": a.model, "L": L, "E": E, "bcT": bool(a.bcT), "ms_per_launch": round(ms, 4),
                   "algorithmic_GB": round(bytes_ / 1e9, 3), "GBps": round(bytes_ / ms / 1e6, 1)}))
