@@ -355,20 +355,24 @@ def run_b200(a):
         sampler.start()
     CF.LAUNCHES = 0
     CF.SCAN_EVENTS = None if graphed else []     # (start, end) CUDA events around every fused-scan launch
+    CF.XPROJ_EVENTS = None if (graphed or train) else []
     ms_dev = timed(step_device, a.steps)
     launches = launches_per_step * a.steps if graphed else CF.LAUNCHES     # a replayed graph re-runs the captured launches
     scan_events, CF.SCAN_EVENTS = (CF.SCAN_EVENTS or []), None
+    xproj_events, CF.XPROJ_EVENTS = (CF.XPROJ_EVENTS or []), None
     ms_e2e = timed(step_e2e, a.steps)
     scan_timed_in = "the timed region"
     if graphed:
         # events cannot be recorded inside a replayed graph: time the scan launches of two EAGER steps after the timed regions
         # (same kernels, same shapes; every rank runs them — the sharded forward exchanges with its peers)
         CF.SCAN_EVENTS = []
+        CF.XPROJ_EVENTS = None if train else []
         barrier()
         for i in range(2):
             eager_device(i)
         torch.cuda.synchronize()
         scan_events, CF.SCAN_EVENTS = CF.SCAN_EVENTS, None
+        xproj_events, CF.XPROJ_EVENTS = (CF.XPROJ_EVENTS or []), None
         scan_timed_in = "2 eager steps after the timed region (the timed steps replay a CUDA graph)"
     if sampler:
         sampler.stop_flag.set()
@@ -413,6 +417,19 @@ def run_b200(a):
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_scan_ms,
                 "launches_timed": len(scan_ms), "timed_in": scan_timed_in,
                 "share_of_step": (avg_scan_ms * a.n_layer) / (ms_dev / a.steps) if scan_ms else None}
+        # second kernel of the step: conv + SiLU -> x_proj -> dt_proj on tcgen05 / TMEM (csrc/xproj.cu), HBM-bound.  Per job and
+        # token it reads x (2E bytes), writes delta (2E bytes) and the fp32 B / C rows state-major (8N bytes) and, for the lane =
+        # channel scan, token-major as well (8N bytes)
+        xp_ms = [s.elapsed_time(e) for s, e in xproj_events]
+        if xp_ms:
+            njobs_launch = a.batch * nstrand * 2
+            xp_bytes = njobs_launch * L_launch * (4 * E + 8 * N * (2 if v_run == 20 else 1))
+            avg_xp = sum(xp_ms) / len(xp_ms)
+            roof["second_kernel"] = {"kernel": "conv_xproj_umma_kernel (tcgen05.mma + TMEM accumulators, TMA in / out)", "bound": "hbm",
+                                     "achieved": xp_bytes / (avg_xp * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": xp_bytes / (avg_xp * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": xp_bytes,
+                                     "avg_launch_ms": avg_xp, "launches_timed": len(xp_ms),
+                                     "share_of_step": (avg_xp * a.n_layer) / (ms_dev / a.steps)}
         # the pipe that actually binds the scan: MUFU ex2, one per (token, channel, state)
         try:
             mufu = CF.microbench(0)

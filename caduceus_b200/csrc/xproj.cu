@@ -515,8 +515,8 @@ extern "C" int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream_) {
   const int64_t ntiles = (a->L + XT - 1) / XT;
   const int sms = cad_sm_count();
   CAD_REQUIRE(sms > 0, "cad_conv_xproj_fwd: no CUDA device");
-  // persistent CTAs: two per SM in total, shared evenly by the jobs (every job has the same number of tiles)
-  int64_t per_job = (2 * (int64_t)sms + a->njobs - 1) / a->njobs;
+  // persistent CTAs: at most two per SM in total (one wave), shared evenly by the jobs (every job has the same number of tiles)
+  int64_t per_job = (2 * (int64_t)sms) / a->njobs;
   if (per_job > ntiles) per_job = ntiles;
   if (per_job < 1) per_job = 1;
   dim3 grid((unsigned)per_job, (unsigned)a->njobs);

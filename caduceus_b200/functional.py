@@ -20,6 +20,7 @@ LAUNCHES = 0          # kernels of THIS library enqueued so far (bench.py report
 SCAN_VARIANT = int(os.environ.get("CAD_SCAN_VARIANT", "0"))         # 0 = choose per call (choose_scan_variant); 3 / 20 = force
 SCAN_NSEG = int(os.environ.get("CAD_SCAN_NSEG", "0"))               # variant 20: time segments per job (0 = default_nseg)
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
+XPROJ_EVENTS = None   # the same around every conv_xproj launch
 
 
 def _launched(n=1):
@@ -281,8 +282,15 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=Fals
         if Lp > L128:
             bcT[:, L128:].zero_()                 # rows no 128-token tile of the kernel covers
         a.bcT, a.ldT = _ptr(bcT), Lp
+    ev = None
+    if XPROJ_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _lib.check(lib.cad_conv_xproj_fwd(C.byref(a), _stream()), "cad_conv_xproj_fwd")
     _launched()
+    if ev is not None:
+        ev[1].record()
+        XPROJ_EVENTS.append(ev)
     return (delta, bc, bcT) if want_bcT else (delta, bc)
 
 
