@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcaduceus_b200.so")
 
 CAD_F32, CAD_F16, CAD_BF16 = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -104,7 +104,7 @@ class ConvXprojArgs(C.Structure):
                 ("seq_of_job", _p), ("pset_of_job", _p), ("rev_of_job", _p), ("halo", _p),
                 ("delta", _p), ("bc", _p),
                 ("L", _i64), ("E", _i64), ("N", _i64), ("R", _i64), ("ldxz", _i64), ("ldd", _i64), ("ldbc", _i64),
-                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bcT", _p), ("ldT", _i64)]
+                ("nseq", _i32), ("njobs", _i32), ("io_dtype", _i32), ("bcT", _p), ("ldT", _i64), ("w_x_packed", _p)]
 
 
 class ConvFwdArgs(C.Structure):

@@ -117,6 +117,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -247,6 +251,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_xproj_umma_kernel(cad_conv_x
     auto request_w = [&](int gw) {                             // slab gw -> slot gw % NS (all lanes call; lanes 0..7 copy)
       const int slot = gw % NS, c0 = (gw % nslab) * KC;
       unsigned char* wb = stages + slot * STAGE_BYTES + XS_BYTES;
+      if (a.w_x_packed) {                                      // pre-packed operand: the slab is one contiguous 3 KB block
+        if (lane == 0) {
+          mbar_expect_tx(&w_full[slot], WX_BYTES);
+          bulk_load_1d(smem_u32(wb), static_cast<const unsigned char*>(a.w_x_packed) + ((size_t)pset * nslab + (gw % nslab)) * WX_BYTES,
+                       WX_BYTES, &w_full[slot]);
+        }
+        __syncwarp();
+        return;
+      }
       if (lane == 0) mbar_expect_tx(&w_full[slot], wbytes);
       __syncwarp();
       if (lane < 4) tma_load_2d(wb + lane * (XPROJ_N / 8 * 128), &maps.w_dt, c0 + 8 * lane, pset * (R + 32), &w_full[slot]);
@@ -482,6 +495,7 @@ extern "C" int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream_) {
   CAD_REQUIRE(aligned16(a->xz) && aligned16(a->w_x) && aligned16(a->delta) && aligned16(a->conv_w) &&
               (a->R != 16 || aligned16(a->w_dt)), "cad_conv_xproj_fwd: alignment");
   CAD_REQUIRE(!a->bcT || (aligned16(a->bcT) && a->ldT >= a->L), "cad_conv_xproj_fwd: bcT must be 16-byte aligned with ldT >= L");
+  CAD_REQUIRE(!a->w_x_packed || aligned16(a->w_x_packed), "cad_conv_xproj_fwd: w_x_packed must be 16-byte aligned");
   CAD_REQUIRE(a->L < ((int64_t)1 << 31) - 1024, "cad_conv_xproj_fwd: sequence too long for 32-bit tensor-map coordinates");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int bf = a->io_dtype == CAD_BF16;

@@ -21,6 +21,8 @@ SCAN_VARIANT = int(os.environ.get("CAD_SCAN_VARIANT", "0"))         # 0 = choose
 SCAN_NSEG = int(os.environ.get("CAD_SCAN_NSEG", "0"))               # variant 20: time segments per job (0 = default_nseg)
 SCAN_EVENTS = None    # when a list: (start, end) CUDA events are recorded around every fused-scan launch
 XPROJ_EVENTS = None   # the same around every conv_xproj launch
+# conv_xproj: hand the kernel W_x pre-packed per slab (pack_w_x, one bulk copy per slab) instead of letting it gather 16-byte rows
+XPROJ_PACK_W = os.environ.get("CAD_XPROJ_PACK_W", "1") == "1"
 
 
 def _launched(n=1):
@@ -258,7 +260,17 @@ def conv_xproj_supported(xz, N, R):
     return xz.dtype in (torch.bfloat16, torch.float16) and N == 16 and 1 <= R <= 16 and E % 64 == 0 and E <= 2048
 
 
-def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=False):
+def pack_w_x(w_x, R):
+    """w_x (P, R+2N, E) -> the per-slab K-major tensor-core operand cad_conv_xproj_args.w_x_packed describes, (P, E/32, 4, 48, 8):
+    dt rows padded to 16 with zeros, then the B / C rows; done once per weight version (derived-weight cache)."""
+    P, rows, E = w_x.shape
+    pad = torch.zeros(P, 48, E, device=w_x.device, dtype=w_x.dtype)
+    pad[:, :R] = w_x[:, :R]
+    pad[:, 16:16 + rows - R] = w_x[:, R:]
+    return pad.view(P, 48, E // 32, 4, 8).permute(0, 2, 3, 1, 4).contiguous()
+
+
+def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=False, w_x_packed=None):
     """Fused conv+SiLU -> x_proj -> dt_proj on tensor cores (tcgen05 + TMEM): returns (delta (njobs, E, ld), bc (njobs, 2N, ldbc)
     fp32) without materialising u.  w_x (P, R+2N, E), w_dt (P, E, R) in the activation dtype.
     want_bcT: also return the B / C rows token-major, (njobs, ceil256(L), 2N) fp32 — what scan variant 20 reads."""
@@ -274,7 +286,7 @@ def conv_xproj(xz, w_x, w_dt, conv_w4, conv_b, jobs, L, halo=None, want_bcT=Fals
     bc = torch.empty(njobs, 2 * N, ldbc, device=xz.device, dtype=torch.float32)
     a = _lib.ConvXprojArgs(_ptr(xz), _ptr(w_x.contiguous()), _ptr(w_dt.contiguous()), _ptr(conv_w4), _ptr(conv_b),
                            _ptr(seq), _ptr(pset), _ptr(rev), _ptr(halo), _ptr(delta), _ptr(bc),
-                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), None, 0)
+                           L, E, N, R, ld, ld, ldbc, nseq, njobs, _dt(xz), None, 0, _ptr(w_x_packed))
     bcT = None
     if want_bcT:
         Lp, L128 = round_up(max(L, 1), 256), round_up(max(L, 1), 128)

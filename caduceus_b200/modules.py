@@ -219,6 +219,7 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
         d["b_in"] = [None if dirs[w].in_proj.bias is None else dirs[w].in_proj.bias.to(act) for w in range(nw)]
         d["w_x"] = torch.stack([m.x_proj.weight.to(act) for m in dirs])                  # (P, R+2N, E)
         d["w_dt"] = torch.stack([m.dt_proj.weight.to(act) for m in dirs])                # (P, E, R)
+        d["w_x_packed"] = CF.pack_w_x(d["w_x"], m0.dt_rank) if (E % 32 == 0 and m0.dt_rank <= 16 and N == 16) else None
         d["packed"] = pack_scan_params(dirs)
         # out_proj per (strand, direction): strand 1 writes the D output channels in reverse order
         w_out = [[(m.out_proj.weight if s == 0 else m.out_proj.weight.flip(0)).to(act) for m in dirs]
@@ -265,10 +266,12 @@ def bimamba_inner(hidden, mamba_fwd, mamba_rev, strategy="add", nstrand=1):
     bcT = None
     if CF.conv_xproj_supported(xz, N, m0.dt_rank) and not _FORCE_UNFUSED_XPROJ:
         # one tensor-core kernel: conv+SiLU -> x_proj -> dt_proj; u never touches HBM
+        wxp = dw["w_x_packed"] if CF.XPROJ_PACK_W else None
         if variant == 20:
-            delta, bc, bcT = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo, want_bcT=True)
+            delta, bc, bcT = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo, want_bcT=True,
+                                           w_x_packed=wxp)
         else:
-            delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo)
+            delta, bc = CF.conv_xproj(xz, dw["w_x"], dw["w_dt"], packed[0], packed[1], jobs, L, halo=halo, w_x_packed=wxp)
     else:
         u = CF.conv_silu(xz, packed[0], packed[1], jobs, L, halo=halo)                    # (njobs, E, Lp)
         wx_job = dw["w_x"].index_select(0, jobs[1].long()) if ndir > 1 else dw["w_x"].expand(u.shape[0], -1, -1)

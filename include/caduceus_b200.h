@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CAD_ABI_VERSION 4
+#define CAD_ABI_VERSION 5
 
 typedef enum { CAD_F32 = 0, CAD_F16 = 1, CAD_BF16 = 2 } cad_dtype;
 
@@ -309,6 +309,10 @@ typedef struct {
   float* bcT;               /* optional (NULL): (njobs, ldT, 2N) fp32, the B / C rows TOKEN-major (scan variant 20), written for
                                tokens [0, min(ldT, ceil128(L))), zeros from L on; the caller zero-fills rows beyond ceil128(L) */
   int64_t ldT;              /* rows per job of bcT (ceil256(L)) */
+  const void* w_x_packed;   /* optional (NULL): w_x rearranged per 32-channel slab into the K-major operand the tensor cores read,
+                               (P, E/32, 4, 48, 8) io dtype = [slab][8-channel group][row][channel in group]; rows [0,R) = dt rows,
+                               [R,16) = zero, [16,48) = B / C rows.  One 3 KB bulk copy per slab then replaces eight tensor-map
+                               boxes of 16-byte rows (measured 14 % of the kernel).  The caller packs it once per weight version. */
 } cad_conv_xproj_args;
 int cad_conv_xproj_fwd(const cad_conv_xproj_args* a, void* stream);
 

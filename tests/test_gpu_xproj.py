@@ -53,11 +53,12 @@ def _restatement(xz, w_x, w_dt, conv_w4, conv_b, spec, L, dtype, halo=None):
     return torch.stack(deltas), torch.stack(bcs)
 
 
-def _run(xz, w_x, w_dt, conv_w4, conv_b, tabs, L, halo, want_bcT=True):
+def _run(xz, w_x, w_dt, conv_w4, conv_b, tabs, L, halo, want_bcT=True, packed=False):
     from caduceus_b200 import functional as CF
     d = lambda t: None if t is None else t.to(DEV).contiguous()   # noqa: E731
+    wxp = CF.pack_w_x(d(w_x), w_dt.shape[-1]) if packed else None
     out = CF.conv_xproj(d(xz), d(w_x), d(w_dt), d(conv_w4), d(conv_b), tuple(d(t) for t in tabs), L, halo=d(halo),
-                        want_bcT=want_bcT)
+                        want_bcT=want_bcT, w_x_packed=wxp)
     torch.cuda.synchronize()
     return out
 
@@ -65,15 +66,16 @@ def _run(xz, w_x, w_dt, conv_w4, conv_b, tabs, L, halo, want_bcT=True):
 SPEC4 = [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0)]
 
 
+@pytest.mark.parametrize("packed", [True, False])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("L,E,R", [(1, 64, 4), (7, 128, 8), (127, 128, 8), (128, 512, 16), (129, 192, 12), (1500, 256, 16),
                                     (3000, 512, 16), (40001, 512, 16), (5000, 1024, 16)])
-def test_xproj_vs_restatement(L, E, R, dtype):
+def test_xproj_vs_restatement(L, E, R, dtype, packed):
     """Ragged lengths around the 128-token tile, d_inner with a 64-channel tail chunk (192), dt_rank < 16 (zero-padded operand
     rows), four jobs mixing sequences, parameter sets and directions — more tiles than persistent CTAs at L = 40001."""
     args = _problem(L, E, R, dtype, SPEC4, 100 + L)
     xz, w_x, w_dt, conv_w4, conv_b, tabs, _ = args
-    delta, bc, bcT = _run(xz, w_x, w_dt, conv_w4, conv_b, tabs, L, None)
+    delta, bc, bcT = _run(xz, w_x, w_dt, conv_w4, conv_b, tabs, L, None, packed=packed)   # packed: W_x handed over pre-arranged per slab
     want_delta, want_bc = _restatement(xz, w_x, w_dt, conv_w4, conv_b, SPEC4, L, dtype)
     rtol, atol = tol(dtype)
     got_bc, got_delta = bc[..., :L].double().cpu(), delta[..., :L].double().cpu()
@@ -112,8 +114,9 @@ def test_xproj_is_deterministic_and_reentrant():
         assert torch.equal(o[2], outs[0][2])
 
 
+@pytest.mark.parametrize("packed", [True, False])
 @pytest.mark.parametrize("tag", ["ps_small", "ph_config0"])
-def test_model_forward_runs_the_tensor_core_projection_kernel(tag):
+def test_model_forward_runs_the_tensor_core_projection_kernel(tag, packed):
     """The bf16 model forward goes through cad_conv_xproj_fwd (not the unfused conv + cuBLAS path) and matches the logits the
     reference's own code produced."""
     import caduceus
@@ -124,14 +127,15 @@ def test_model_forward_runs_the_tensor_core_projection_kernel(tag):
     model.load_state_dict(fx["state_dict"])
     model = model.to(DEV).to(torch.bfloat16).eval()
     calls = []
-    lib_fn = CF.conv_xproj
+    lib_fn, prev = CF.conv_xproj, CF.XPROJ_PACK_W
     try:
-        CF.conv_xproj = lambda *a, **k: calls.append(1) or lib_fn(*a, **k)
+        CF.XPROJ_PACK_W = packed
+        CF.conv_xproj = lambda *a, **k: calls.append(k.get("w_x_packed") is not None) or lib_fn(*a, **k)
         with torch.no_grad():
             logits = model(fx["input_ids"].to(DEV)).logits.float().cpu()
     finally:
-        CF.conv_xproj = lib_fn
-    assert len(calls) == cfg.n_layer
+        CF.conv_xproj, CF.XPROJ_PACK_W = lib_fn, prev
+    assert len(calls) == cfg.n_layer and all(c == packed for c in calls)
     ref = fx["logits"].float()
     rtol, atol = tol(torch.bfloat16)
     scale = ref.abs().max().item()
