@@ -38,7 +38,8 @@ def main():
     raw = _page(a.report, "raw")
     d = {h: v for h, v in zip(raw[0], raw[2])}
     print("kernel:", d.get("Kernel Name", "?"))
-    print(f"duration {_f(d['gpu__time_duration.sum']):.4f} ms   grid {d['launch__grid_size']} x {d['launch__block_size']} threads, "
+    units = {h: u for h, u in zip(raw[0], raw[1])}
+    print(f"duration {_f(d['gpu__time_duration.sum']):.4f} {units.get('gpu__time_duration.sum', 'ms')}   grid {d['launch__grid_size']} x {d['launch__block_size']} threads, "
           f"{d['launch__registers_per_thread']} regs")
     print(f"issue slots {_f(d['smsp__issue_active.avg.pct_of_peak_sustained_active']):.1f} %   "
           f"MUFU {_f(d['sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active']):.1f} %   "
