@@ -226,3 +226,23 @@ def test_segment_count_of_the_lane_per_channel_scan():
         assert CF.default_nseg(4, 512, 131072, 8) == 9
     finally:
         CF.SCAN_NSEG = old
+
+
+def test_pack_w_x_is_the_per_slab_tensor_core_operand():
+    """functional.pack_w_x: (P, R+2N, E) -> (P, E/32, 4, 48, 8) = [slab][8-channel group][operand row][channel in group], dt rows
+    padded to 16 with zeros, then the B / C rows — the layout cad_conv_xproj_args.w_x_packed documents (include/caduceus_b200.h)
+    and csrc/xproj.cu copies slab by slab (3072 bytes each) straight into the K-major UMMA operand."""
+    from caduceus_b200 import functional as CF
+    for R in (4, 8, 16):
+        P, E = 2, 128
+        w = torch.arange(P * (R + 32) * E, dtype=torch.float32).view(P, R + 32, E) + 1
+        packed = CF.pack_w_x(w.to(torch.bfloat16), R)
+        assert packed.shape == (P, E // 32, 4, 48, 8) and packed.is_contiguous()
+        assert packed[0, 0].numel() * packed.element_size() == 3072
+        wb = w.to(torch.bfloat16)
+        for p in range(P):
+            for row in range(48):
+                src = row if row < R else (None if row < 16 else row - 16 + R)
+                got = packed[p, :, :, row, :].reshape(E)          # channel = slab * 32 + group * 8 + j
+                want = torch.zeros(E, dtype=torch.bfloat16) if src is None else wb[p, src]
+                assert torch.equal(got, want), (R, p, row)
