@@ -246,3 +246,19 @@ def test_pack_w_x_is_the_per_slab_tensor_core_operand():
                 got = packed[p, :, :, row, :].reshape(E)          # channel = slab * 32 + group * 8 + j
                 want = torch.zeros(E, dtype=torch.bfloat16) if src is None else wb[p, src]
                 assert torch.equal(got, want), (R, p, row)
+
+
+def test_library_sass_holds_the_blackwell_tensor_core_and_tma_paths():
+    """The built .so carries what DESIGN.md §4.2 claims for the projection kernel: tcgen05.mma (UTCHMMA), TMEM loads (LDTM), TMA
+    tensor loads and stores (UTMALDG / UTMASTG), bulk copies (UBLKCP) — and no legacy warp-level HMMA left in the library."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from caduceus_b200.build import LIB, build
+    build()
+    sass = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass
