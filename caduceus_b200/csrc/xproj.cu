@@ -1,24 +1,32 @@
 // Fused  (anti)causal depthwise conv + SiLU  ->  x_proj  ->  dt_proj  on the 5th-generation tensor cores (tcgen05.mma,
-// accumulators in tensor memory) for sm_100a.  Same contract as conv_xproj_kernel (xproj.cu): replaces, per job, the chain
-// causal_conv1d_fwd -> F.linear(x_proj) -> dt_proj.weight @ x_dbl[:R]  of upstream's `mamba_inner_fn` (SURVEY.md A.1,
-// reached from ref:caduceus/modeling_caduceus.py:128-133) and writes what the scan consumes (delta, bc, optionally bcT).
+// accumulators in tensor memory) for sm_100a: replaces, per job, the chain  causal_conv1d_fwd -> F.linear(x_proj) ->
+// dt_proj.weight @ x_dbl[:R]  of upstream's `mamba_inner_fn` (reached from
+// ref:caduceus/modeling_caduceus.py:128-133) and writes what the scan consumes (delta, bc, optionally bcT); u = silu(conv(x))
+// never touches HBM.  Contract: cad_conv_xproj_args in include/caduceus_b200.h.
 //
-// Both projections are issued by ONE thread per CTA; the other 255 only convolve and move data:
+// The two projections, per 128-token tile:
 //   x_proj :  D1[128 tokens x 48]   += u^T[128 x 32] . W_x[48 x 32]^T      per 32-channel slab, 2 x (M128 N48 K16)
 //             A = the u slab exactly as the conv threads produce it (channel-major rows of 8 tokens = an MN-major
-//             operand of 8x8 core matrices, no swizzle), B = the W_x slab (K-major); D1 in TMEM columns [0, 48),
+//             operand of 8x8 core matrices, no swizzle), B = the W_x slab (K-major); D1 in TMEM columns [64 (tile & 1), +48),
 //             TMEM lane = token: the B / C rows leave as coalesced fp32 rows, the dt rows go back to shared memory.
 //   dt_proj:  D2[128 channels x 128 tokens] = W_dt[chunk, 0:16] . bf16(x_dbl[:, 0:16])^T   per 128-channel chunk, one M128 N128 K16
 //             A = W_dt resident in shared memory (K-major), B = the dt rows of D1 rounded to the io dtype (the reference's
-//             rounding point), K-major; D2 double-buffered in TMEM columns [0,128) / [128,256).  TMEM lane = channel: a
-//             thread reads 32 consecutive tokens of one delta row and stores them as four 16-byte vectors.
+//             rounding point), K-major; D2 in TMEM columns [128, 256).  TMEM lane = channel: a thread reads 32 consecutive
+//             tokens of one delta row; the warp stages (32 channels x 32 tokens) with the 64-byte swizzle and one lane stores
+//             the block with a bulk tensor copy.
 //
-// CTA = 256 threads, persistent over the 128-token tiles of one job (grid.x CTAs per job, 2 CTAs per SM: 256 of the 512
-// TMEM columns each); W_dt and the conv taps are loaded once per CTA.  The K loop never drains between tiles: each x slab
-// (32 channels x 152 tokens with the conv aprons) is ONE bulk tensor copy (TMA, zero fill outside the sequence) into a
-// 4-slot ring three slabs ahead, signalled on an mbarrier; the W_x slab follows through cp.async.  ONE __syncthreads per
-// slab publishes the u slab to the tensor core; a u buffer is rewritten only after the mbarrier its MMAs committed to.
-// First hardware run, descriptor probe and the profile that shaped this version: profiles/r2_call13_umma_first_hw_run.log.
+// CTA = 14 warps with fixed roles, persistent over the tiles of one job (grid.x CTAs per job, 2 CTAs per SM: 256 of the 512 TMEM
+// columns each); W_dt and the conv taps are loaded once per CTA.  A 3-stage ring holds per K slab the raw x box (32 channels x
+// 152 tokens with the conv aprons: ONE bulk tensor copy, zero fill outside the sequence), the W_x slab (one 3 KB bulk copy of the
+// host-packed operand, or eight tensor-map boxes when the caller did not pack it) and the u slab.
+//   warp 8      requests x slabs as soon as the conv warps hold a slot's samples in registers (x_empty -> x_full)
+//   warps 0-7   convolve: x_full -> LDS -> x_empty;  slab_done (u slot free) -> FFMA / tanh -> STS -> proxy fence -> u_full
+//   warp 9      w_full + u_full -> lane 0 issues the MMAs -> tcgen05.commit to slab_done (and acc_full after a tile's last slab);
+//               requests the W_x slab two slabs ahead
+//   warps 10-13 acc_full -> tcgen05.ld x_dbl -> B / C rows out, dt operand -> acc_empty;  dt_proj per chunk (bar.sync among the
+//               four) -> dt_full -> tcgen05.ld -> staged block -> TMA store
+// Hand-over is mbarriers only; the CTA-wide barriers are set-up and tear-down.  History and measurements: DESIGN.md §4.2,
+// profiles/r2_call13..25*, descriptor probe scripts/umma_probe.cu.
 #include "common.cuh"
 #include "scan_common.cuh"
 
