@@ -262,3 +262,51 @@ def test_library_sass_holds_the_blackwell_tensor_core_and_tma_paths():
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass
+
+
+def test_operator_level_shim_binds_the_references_own_model_code(monkeypatch):
+    """INTEGRATION.md §2 executed: the reference's OWN caduceus/*.py (loaded from /root/reference, build container only) on top
+    of a `mamba_ssm` shim that re-exports caduceus_b200.modules — the five symbols the reference imports
+    (ref:caduceus/modeling_caduceus.py:11-27, ref:caduceus/modeling_rcps.py:12-18).  The model constructs with the reference's
+    constructor calls, loads a reference-generated checkpoint strictly, is built from this library's operators, and — there being
+    no GPU here and no CPU fallback — its forward fails loudly at the first kernel call instead of computing something else."""
+    import sys
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from ref_loader import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("the reference tree exists only in the build container")
+    from caduceus_b200 import modules as M
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import golden
+    for name in ("mamba_ssm", "mamba_ssm.modules", "mamba_ssm.ops", "mamba_ssm.ops.triton"):
+        pkg = types.ModuleType(name)
+        pkg.__path__ = []
+        monkeypatch.setitem(sys.modules, name, pkg)
+    simple = types.ModuleType("mamba_ssm.modules.mamba_simple")
+    simple.Mamba, simple.Block = M.Mamba, M.Block
+    lnorm = types.ModuleType("mamba_ssm.ops.triton.layernorm")
+    lnorm.RMSNorm, lnorm.rms_norm_fn, lnorm.layer_norm_fn = M.RMSNorm, M.rms_norm_fn, M.layer_norm_fn
+    monkeypatch.setitem(sys.modules, simple.__name__, simple)
+    monkeypatch.setitem(sys.modules, lnorm.__name__, lnorm)
+    name = "ref_caduceus_on_b200_operators"
+    ref = load_reference(name)
+    try:
+        for tag in ("ps_small", "ph_config0"):       # RCPS: the reference's own RCPSMambaBlock around our Mamba; Ph: our Block too
+            fx = golden(f"model_{tag}.pt")
+            cfg = ref.configuration_caduceus.CaduceusConfig(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in fx["config"].items()})
+            model = ref.modeling_caduceus.CaduceusForMaskedLM(cfg).eval()
+            model.load_state_dict(fx["state_dict"], strict=True)
+            assert type(model).__module__ == f"{name}.modeling_caduceus"      # the reference's class, not this repo's drop-in
+            assert len(model.caduceus.backbone.layers) == cfg.n_layer
+            mambas = [m for m in model.modules() if isinstance(m, M.Mamba)]
+            assert len(mambas) >= cfg.n_layer                                 # every mixer is this library's operator
+            if not cfg.rcps:
+                assert all(isinstance(b, M.Block) for b in model.caduceus.backbone.layers)
+            if not torch.cuda.is_available():
+                with pytest.raises(RuntimeError, match="no CPU fallback"):
+                    with torch.no_grad():
+                        model(fx["input_ids"])
+    finally:
+        for k in [k for k in sys.modules if k == name or k.startswith(name + ".")]:
+            del sys.modules[k]
